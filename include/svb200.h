@@ -8,6 +8,7 @@
  */
 #ifndef SVB200_H
 #define SVB200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -30,6 +31,74 @@ const char* svb_last_error(void);
  * nn.LSTM / nn.Linear issue for speech_embedder_net.py:28,31. */
 int svb_gemm_bf16(const void* const* A, const void* const* B, int nterms, float* C, const float* bias, int M, int N,
                   int K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn, int b_mn, void* stream);
+
+/* ---- SpeechEmbedder (speech_embedder_net.py:15-33): 3-layer LSTM + last-frame Linear + L2 norm ------------------
+ * Dimensions: B utterances, T frames, I mel bins, H hidden (multiple of 128), L layers (<= 8), P projection size. */
+
+/* Bytes of the packed bf16 weight shadow and of the per-call workspace (training != 0 keeps the BPTT stash). */
+int svb_embedder_sizes(int B, int T, int I, int H, int L, int P, int training, size_t* packed_bytes,
+                       size_t* workspace_bytes);
+
+/* Re-pack the fp32 master parameters of nn.LSTM (state_dict order: weight_ih, weight_hh, bias_ih, bias_hh per layer;
+ * HOST array of 4L DEVICE pointers; speech_embedder_net.py:19-24) into gate-interleaved bf16 hi/lo shadows. */
+int svb_embedder_pack_weights(const float* const* params, void* packed, int I, int H, int L, void* stream);
+
+/* SpeechEmbedder.forward (speech_embedder_net.py:27-33). x: (B,T,I) batch-first, x_dtype 0=float32 1=float64
+ * (":28 x.float()"); emb: (B,P) float32 unit rows.  rec_terms 1..3 = number of split-bf16 terms of the recurrent
+ * GEMM (1: h_hi W_hi; 2: + h_hi W_lo; 3: + h_lo W_hi).  With training != 0 the workspace afterwards holds the stash that
+ * svb_embedder_backward consumes. */
+int svb_embedder_forward(const void* x, int x_dtype, const void* packed, const float* proj_w, const float* proj_b,
+                         float* emb, void* workspace, int B, int T, int I, int H, int L, int P, int training,
+                         int rec_terms, void* stream);
+
+/* BPTT for loss.backward() (train_speech_embedder.py:62).  demb: (B,P) dL/d(embeddings).  grads: HOST array of 4L+2
+ * DEVICE pointers (nn.LSTM order, then projection.weight, projection.bias), fp32, parameter layout; overwritten. */
+int svb_embedder_backward(const float* demb, const void* packed, const float* proj_w, float* const* grads,
+                          void* workspace, int B, int T, int I, int H, int L, int P, void* stream);
+
+/* ---- GE2E loss (speech_embedder_net.py:35-49, utils.py:27-132) ---------------------------------------------------- */
+
+int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);
+
+/* One fused kernel for get_centroids + get_utterance_centroids + get_cossim (+ w*cos+b, calc_loss and all gradients).
+ *   E (N,M,D); Cext (Nc,D) foreign centroids or NULL (centroids of E, Nc == N);
+ *   w,b device scalars (NULL,NULL: cosine matrix only); dcos (N,M,Nc) upstream gradient for get_cossim's backward;
+ *   gscale device scalar multiplying every gradient or NULL.
+ * Outputs (any may be NULL): cos_out (N,M,Nc) incl. the +1e-6 of utils.py:114; per_out (N,M) per-embedding loss;
+ *   loss_out scalar (SUM, utils.py:131); dE (N,M,D); dCext (Nc,D); dw, db scalars.
+ * fused != 0: single cooperative launch; 0: one launch per phase (debug). */
+int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w, const float* b,
+             const float* dcos, const float* gscale, float* cos_out, float* per_out, float* loss_out, float* dE,
+             float* dCext, float* dw, float* db, void* workspace, size_t workspace_bytes, int fused, void* stream);
+
+/* utils.get_centroids (utils.py:27-29) and its backward. */
+int svb_centroids(const float* E, float* C, int N, int M, int D, void* stream);
+int svb_centroids_bwd(const float* dC, float* dE, int N, int M, int D, void* stream);
+
+/* utils.calc_loss (utils.py:126-132) on a caller-supplied similarity matrix S (N,M,Nc); dS optional. */
+int svb_calc_loss(const float* S, int N, int M, int Nc, float* per_out, float* loss_out, float* dS,
+                  const float* gscale, void* stream);
+
+/* x[i] *= *g for three buffers in one launch (autograd's upstream scalar). */
+int svb_scale3(float* a, size_t na, float* b, size_t nb, float* c, size_t nc, const float* g, void* stream);
+
+/* ---- TI-SV EER sweep (train_speech_embedder.py:132-149) ---------------------------------------------------------- */
+
+/* Exact integer counts of sim > thresholds[t] for speakers [speaker0, speaker0+n_local): sim (n_local, Mv, Nc) float32,
+ * thresholds ascending float32 (device, T <= 128); cnt_all/cnt_diag (n_local, T) int32. */
+int svb_eer_counts(const float* sim, int n_local, int Mv, int Nc, int speaker0, const float* thresholds, int T,
+                   int* cnt_all, int* cnt_diag, void* stream);
+/* Reference float32 arithmetic on the counts of all N speakers -> out[0..3] = EER, selected threshold index (-1: none),
+ * FAR, FRR; out[4..4+T) = FAR per threshold, out[4+T..4+2T) = FRR per threshold. */
+int svb_eer_finish(const int* cnt_all, const int* cnt_diag, int N, int Mv, int T, float* out, void* stream);
+
+/* ---- d-vector extraction (dvector_create.py:48-52,98-99 and :55-73) ----------------------------------------------- */
+
+/* Sliding windows of a (nmels, Ttot) log-mel matrix (row pitch ldS) -> (W, win, nmels); win_start (W) int32 device. */
+int svb_dvector_windows(const float* S, int64_t ldS, int nmels, const int* win_start, int W, int win, float* out,
+                        void* stream);
+/* align_embeddings: out[p,:] = float64(mean over rows [seg_offsets[p], seg_offsets[p+1]) of emb (W,D) float32). */
+int svb_segment_mean(const float* emb, int D, const int* seg_offsets, int P, double* out, void* stream);
 
 #ifdef __cplusplus
 }

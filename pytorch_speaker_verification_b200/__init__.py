@@ -3,4 +3,7 @@
 Drop-in for hwidong-na/PyTorch_Speaker_Verification's ``speech_embedder_net`` / ``utils`` loss API,
 backed by hand-written CUDA kernels behind the C ABI in include/svb200.h.  No CPU fallback.
 """
-__all__ = ["_lib"]
+from .speech_embedder_net import GE2ELoss, SpeechEmbedder            # noqa: F401
+from .utils import calc_loss, get_centroids, get_cossim              # noqa: F401
+from .eer import compute_eer, eer_sweep                              # noqa: F401
+from .dvector import align_embeddings, extract_dvectors, get_windows  # noqa: F401

@@ -12,10 +12,12 @@ struct EpiStoreF32 {
     const float* bias;   // may be null
     int64_t ldc;
     int N;
+    int unpack_H;        // > 0: row m is a packed gate row (see lstm.cuh); store to row gate*H + unit
   };
   struct Tile {};
   static __device__ __forceinline__ void prologue(const Params&, Tile&, int, int, bool) {}
   static __device__ __forceinline__ void apply(const Params& p, Tile&, int m, int n0, float (&acc)[32]) {
+    if (p.unpack_H > 0) m = ((m & 31) >> 3) * p.unpack_H + (m >> 5) * 8 + (m & 7);
     float* dst = p.C + (int64_t)m * p.ldc + n0;
     if (n0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll

@@ -63,7 +63,7 @@ extern "C" int svb_gemm_bf16(const void* const* A, const void* const* B, int nte
     e = make_operand_map(&ops.tb[t], B[t], N, K, ldb, b_mn, 128);
     if (e) return e;
   }
-  EpiStoreF32::Params ep{C, bias, ldc, N};
+  EpiStoreF32::Params ep{C, bias, ldc, N, 0};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t err;
   if (!a_mn && !b_mn) err = launch_tc_gemm<128, 4, false, false, EpiStoreF32>(ops, ep, s);

@@ -1,0 +1,310 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): embeddings 1e-3 per-vector L2-relative (bf16 recurrent GEMM, fp32
+accumulate); GE2E loss / dE / dw 1e-5 relative (fp32); db against the float64 oracle (the fp32
+reference itself is 1.7 % off there); EER bit-exact given identical similarity scores; LSTM parameter gradients
+(bf16 BPTT operands, no tolerance stated by north_star) 3e-2 per-tensor L2-relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _inputs as I
+from oracle import dvector as odv
+from oracle import eer as oeer
+from oracle import embedder as oemb
+from oracle import ge2e as oge2e
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def svb():
+    import pytorch_speaker_verification_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def net(svb):
+    torch.manual_seed(0)
+    n = svb.SpeechEmbedder().cuda()
+    g = load("embedder_c1.npz")
+    sums = [float(v.double().sum()) for v in n.state_dict().values()]
+    np.testing.assert_allclose(sums, g["w_sum"], atol=1e-9, rtol=0)     # same init as the reference's
+    return n
+
+
+# ----------------------------------------------------------------------------------------------- GE2E
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", list(I.GE2E_CASES))
+def test_ge2e_loss_and_gradients(svb, name, fused):
+    N, M, D, kind, w0, b0 = I.GE2E_CASES[name]
+    g = load(f"ge2e_{name}.npz")
+    Enp = I.ge2e_embeddings(N, M, D, kind)
+    E = torch.tensor(Enp, device="cuda", requires_grad=True)
+    crit = svb.GE2ELoss("cuda")
+    crit.fused = fused
+    with torch.no_grad():
+        crit.w.fill_(w0)
+        crit.b.fill_(b0)
+    loss = crit(E)
+    loss.backward()
+    o32 = oge2e.ge2e_fwd_bwd(Enp, w0, b0)
+    assert rel(loss.item(), g["loss_f32"]) < 1e-5 and rel(loss.item(), g["loss_f64"]) < 1e-5
+    assert rel(loss.item(), o32["loss"]) < 1e-5
+    assert rel(E.grad.cpu().numpy(), g["dE_f64"]) < 1e-5
+    assert rel(E.grad.cpu().numpy(), o32["dE"]) < 1e-5
+    assert rel(crit.w.grad.item(), g["dw_f64"]) < 1e-5
+    assert rel(crit.b.grad.item(), g["db_f64"]) < 2e-3     # ill-conditioned; fp32 reference is ~2e-2 off
+
+
+def test_ge2e_upstream_scale_and_no_grad(svb):
+    N, M, D, kind, w0, b0 = I.GE2E_CASES["c1"]
+    Enp = I.ge2e_embeddings(N, M, D, kind)
+    E = torch.tensor(Enp, device="cuda", requires_grad=True)
+    crit = svb.GE2ELoss("cuda")
+    (crit(E) * 0.25).backward()
+    o = oge2e.ge2e_fwd_bwd(Enp, 10.0, -5.0)
+    assert rel(E.grad.cpu().numpy(), 0.25 * o["dE"]) < 1e-5
+    assert rel(crit.w.grad.item(), 0.25 * o["dw"]) < 1e-5
+    with torch.no_grad():
+        l2 = crit(E)
+    assert rel(l2.item(), o["loss"]) < 1e-5 and not l2.requires_grad
+    with pytest.raises(ValueError):
+        crit(torch.randn(3, 1, 8, device="cuda"))          # M = 1: the reference divides by zero
+
+
+def test_ge2e_large_w_is_stable(svb):
+    """exp(S) overflows fp32 in the reference once w + b > 88; the kernel's max-subtraction must give the
+    float64 value (quirk 4)."""
+    enr, ver = I.eer_embeddings(16, 6, 0.06, 0.3, 99)       # overlapping speakers: cos ~0.9 everywhere
+    Enp = np.concatenate([enr, ver], axis=1)
+    crit = svb.GE2ELoss("cuda")
+    with torch.no_grad():
+        crit.w.fill_(100.0)
+        crit.b.fill_(20.0)                                    # S ~ 110 > 88: exp overflows in fp32
+    E = torch.tensor(Enp, device="cuda", requires_grad=True)
+    loss = crit(E)
+    loss.backward()
+    o = oge2e.ge2e_fwd_bwd(Enp.astype(np.float64), 100.0, 20.0)
+    assert o["loss"] > 10 and np.isfinite(loss.item())
+    assert rel(loss.item(), o["loss"]) < 1e-4
+    assert rel(E.grad.cpu().numpy(), o["dE"]) < 1e-4
+
+
+def test_free_functions_match_reference_api(svb):
+    """get_centroids / get_cossim / calc_loss (utils.py) forward and autograd, incl. foreign centroids."""
+    g = load("toy.npz")
+    E = torch.tensor(g["E"], device="cuda")
+    C = svb.get_centroids(E)
+    np.testing.assert_array_equal(C.cpu().numpy(), g["centroids"])
+    cos = svb.get_cossim(E, C)
+    np.testing.assert_allclose(cos.cpu().numpy(), g["cossim"], atol=2e-7, rtol=0)
+    loss, per = svb.calc_loss(1.0 * cos + 0.0)
+    np.testing.assert_allclose(per.cpu().numpy(), g["per"], rtol=1e-6)
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-6)
+    # autograd through the three free functions == closed form
+    N, M, D, kind, w0, b0 = I.GE2E_CASES["nonunit"]
+    Enp = I.ge2e_embeddings(N, M, D, kind)
+    Et = torch.tensor(Enp, device="cuda", requires_grad=True)
+    w = torch.tensor(w0, device="cuda", requires_grad=True)
+    b = torch.tensor(b0, device="cuda", requires_grad=True)
+    S = w * svb.get_cossim(Et, svb.get_centroids(Et)) + b
+    l, _ = svb.calc_loss(S)
+    l.backward()
+    o = oge2e.ge2e_fwd_bwd(Enp, w0, b0)
+    assert rel(l.item(), o["loss"]) < 1e-5
+    assert rel(Et.grad.cpu().numpy(), o["dE"]) < 2e-5
+    assert rel(w.grad.item(), o["dw"]) < 2e-5
+    # CPU tensors are accepted and come back on the CPU
+    cos_cpu = svb.get_cossim(torch.tensor(Enp), svb.get_centroids(torch.tensor(Enp)))
+    assert cos_cpu.device.type == "cpu"
+    np.testing.assert_allclose(cos_cpu.numpy(), oge2e.get_cossim(Enp, oge2e.get_centroids(Enp)), atol=3e-6)
+
+
+# ----------------------------------------------------------------------------------------------- EER
+@pytest.mark.parametrize("name", list(I.EER_CASES))
+def test_eer_bit_exact(svb, name):
+    g = load("eer.npz")
+    N, M, sigma, alpha, seed = I.EER_CASES[name]
+    enr, ver = I.eer_embeddings(N, M, sigma, alpha, seed)
+    exp = [float(v) for v in g[f"{name}.tuple"]]
+    if f"{name}.sim" in g:        # identical similarity scores in -> bit-exact tuple out
+        got = svb.eer_sweep(torch.tensor(g[f"{name}.sim"]))
+        assert [float(v) for v in got] == exp
+        ca, cd = oeer.eer_counts(g[f"{name}.sim"])
+        from pytorch_speaker_verification_b200 import eer as E, ops
+        sim = torch.tensor(g[f"{name}.sim"], device="cuda")
+        gca, gcd = ops.eer_counts(sim, E._thresholds_f32(sim.device, E.THRESHOLDS))
+        np.testing.assert_array_equal(gca.cpu().numpy().T, ca)
+        np.testing.assert_array_equal(gcd.cpu().numpy().T, cd)
+    # end to end from embeddings (own similarity kernel): same tuple as the oracle fed the kernel's sim
+    (tup, sim) = svb.compute_eer(torch.tensor(enr, device="cuda"), torch.tensor(ver, device="cuda"))
+    sim_o = oge2e.get_cossim(ver, oge2e.get_centroids(enr))
+    np.testing.assert_allclose(sim.cpu().numpy(), sim_o, atol=3e-6, rtol=0)
+    assert [float(v) for v in tup] == [float(v) for v in oeer.eer_sweep(sim.cpu().numpy())]
+    np.testing.assert_allclose([float(v) for v in tup], exp, atol=5e-3)
+
+
+def test_eer_threshold_rounding_and_scale(svb):
+    t = oeer.THRESHOLDS[7]
+    sim = torch.full((2, 1, 2), float(np.float32(t)), dtype=torch.float32)
+    from pytorch_speaker_verification_b200 import eer as E, ops
+    sg = sim.cuda()
+    ca, _ = ops.eer_counts(sg, E._thresholds_f32(sg.device, E.THRESHOLDS))
+    assert ca[:, 7].sum().item() == 0 and ca[:, 6].sum().item() == 4
+    # BASELINE config 5 size through size-independent properties: counts monotone in the threshold,
+    # diagonal counts <= Mv, totals match a float64 numpy recount on a sample of thresholds
+    N, Mv = 1024, 3
+    enr, ver = I.eer_embeddings(N, 6, 0.06, 0.5, 4242)
+    tup, sim = svb.compute_eer(torch.tensor(enr, device="cuda"), torch.tensor(ver, device="cuda"))
+    ca, cd = ops.eer_counts(sim, E._thresholds_f32(sim.device, E.THRESHOLDS))
+    ca, cd = ca.cpu().numpy(), cd.cpu().numpy()
+    assert (np.diff(ca, axis=1) <= 0).all() and (np.diff(cd, axis=1) <= 0).all() and cd.max() <= Mv
+    s = sim.cpu().numpy()
+    for ti in (0, 13, 49):
+        assert ca[:, ti].sum() == int((s > np.float32(oeer.THRESHOLDS[ti])).sum())
+    assert [float(v) for v in tup] == [float(v) for v in oeer.eer_sweep(s)]
+
+
+# ----------------------------------------------------------------------------------------------- d-vectors
+def test_dvector_windows_alignment(svb):
+    g = load("dvector.npz")
+    for T in (37, 160):
+        p = np.sqrt(I.power_spec(T, seed=T)) ** 2
+        S = np.log10(np.dot(np.eye(40, dtype=np.float32), p) + 1e-6).astype(np.float32)
+        np.testing.assert_array_equal(svb.get_windows(torch.tensor(S)).numpy(), g[f"win_T{T}"])
+    assert tuple(svb.get_windows(torch.zeros(40, 24)).shape) == (0, 24, 40)
+    for W in (1, 2, 3, 5, 13, 30, 82):
+        out = svb.align_embeddings(I.unit_rows(W, 256, seed=W))
+        assert out.dtype == np.float64
+        np.testing.assert_array_equal(out, g[f"align_W{W}"])
+    from pytorch_speaker_verification_b200 import dvector as D
+    for T in list(range(0, 80)) + [160, 180, 301, 1000]:
+        assert list(D.window_starts(T)) == odv.window_starts(T)
+    for W in range(0, 90):
+        offs = D.partition_offsets(W)
+        if W:
+            assert [(int(a), int(b)) for a, b in zip(offs[:-1], offs[1:])] == odv.partitions(W)
+
+
+def test_extract_dvectors_batched_equals_per_file(svb, net):
+    rng = np.random.RandomState(5)
+    specs = [np.log10(I.power_spec(int(T), seed=int(T)) + 1e-6).astype(np.float32) for T in (20, 61, 130, 300)]
+    outs = svb.extract_dvectors(net, specs)
+    assert outs[0].shape == (0, 256)
+    for S, o in zip(specs[1:], outs[1:]):
+        with torch.no_grad():
+            emb = net(svb.get_windows(torch.tensor(S)))                       # dvector_create.py:98-100 per file
+        np.testing.assert_allclose(o, svb.align_embeddings(emb.cpu().numpy()), atol=2e-6)
+        ref = odv.align_embeddings(emb.cpu().numpy())
+        np.testing.assert_array_equal(svb.align_embeddings(emb.cpu().numpy()), ref)
+
+
+# ----------------------------------------------------------------------------------------------- embedder
+def emb_err(a, b):
+    return (np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)).max()
+
+
+def test_embedder_forward_matches_reference(svb, net):
+    g = load("embedder_c1.npz")
+    x = torch.tensor(I.logmel(20, 180, seed=1234))
+    with torch.no_grad():
+        e = net(x.cuda()).cpu().numpy()
+        e24 = net(torch.tensor(I.logmel(7, 24, seed=4321)).cuda()).cpu().numpy()
+        e64 = net(x[:3].double())                     # float64 CPU input: staged, computed in fp32, back on CPU
+    assert emb_err(e, g["emb"]) < 1e-3, emb_err(e, g["emb"])
+    assert emb_err(e24, g["emb_T24"]) < 1e-3
+    assert e64.device.type == "cpu" and e64.dtype == torch.float32
+    assert emb_err(e64.numpy(), g["emb_from_f64_input"]) < 1e-3
+    np.testing.assert_allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+    print("embedding err C1:", emb_err(e, g["emb"]), "T24:", emb_err(e24, g["emb_T24"]))
+
+
+def test_embedder_saturated_weights(svb):
+    g = load("embedder_saturated.npz")
+    sat = I.saturating_weights({k: v.numpy() for k, v in oemb.init_state_dict(seed=0).items()})
+    n = svb.SpeechEmbedder().cuda()
+    n.load_state_dict({k: torch.tensor(v) for k, v in sat.items()})
+    x = torch.tensor(I.logmel(20, 180, seed=1234)).cuda()
+    errs = {}
+    for terms in (1, 2, 3):
+        n.recurrent_terms = terms
+        with torch.no_grad():
+            errs[terms] = emb_err(n(x).cpu().numpy(), g["emb"])
+    print("embedding err, weights x2.5, recurrent terms 1/2/3:", errs)
+    # x2.5 weights amplify the bf16 rounding of W_hh (CPU emulation: 3.2e-3 / 1.0e-3 / 8e-6); the split-bf16
+    # recurrent GEMM restores the 1e-3 bar, the default single term stays within 5e-3 on this stress case
+    assert errs[3] < 1e-3 and errs[2] < 2e-3 and errs[1] < 5e-3, errs
+
+
+def test_embedder_batch_independence_and_ragged_batch(svb, net):
+    """Rows are independent (the caller's permutation at train_speech_embedder.py:48-57 is a no-op) and a batch
+    that is not a multiple of the 128-row tile gives the same rows as a padded one."""
+    x = torch.tensor(I.logmel(150, 40, seed=9)).cuda()
+    with torch.no_grad():
+        full = net(x)
+        perm = torch.randperm(150, device="cuda")
+        assert torch.equal(net(x[perm]), full[perm])
+        assert torch.equal(net(x[:37]), full[:37])
+
+
+def test_train_step_gradients(svb, net):
+    """Full C1 train step (embedder + GE2E) against the explicit-cell oracle's autograd."""
+    g = load("embedder_c1.npz")
+    x = torch.tensor(I.logmel(20, 180, seed=1234))
+    crit = svb.GE2ELoss("cuda")
+    net.zero_grad()
+    emb = net(x.cuda())
+    loss = crit(emb.reshape(4, 5, -1))
+    loss.backward()
+    assert rel(loss.item(), g["loss"]) < 1e-3           # loss through bf16 embeddings
+    sd = {k: v.clone().requires_grad_(True) for k, v in oemb.init_state_dict(seed=0).items()}
+    e_o = oemb.embedder_explicit(x, sd)
+    w = torch.tensor(10.0, requires_grad=True)
+    b = torch.tensor(-5.0, requires_grad=True)
+    oemb.library_ge2e_loss(e_o.reshape(4, 5, -1), w, b).backward()
+    errs = {}
+    for k, p in net.named_parameters():
+        go = sd[k].grad.numpy()
+        assert abs(np.linalg.norm(go) - float(g[f"gnorm.{k}"])) < 2e-3 * float(g[f"gnorm.{k}"])   # oracle == reference
+        errs[k] = rel_l2(p.grad.cpu().numpy(), go)
+    print("per-tensor grad rel-L2:", {k: round(float(v), 4) for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e < (1e-1 if "bias" in k else 3e-2), (k, e)
+    assert rel(crit.w.grad.item(), w.grad.item()) < 2e-2
+
+
+def test_state_dict_roundtrip_and_cpu_module(svb):
+    """Checkpoints are wire-compatible with the reference (14 keys) and a module left on the CPU (test(),
+    dvector_create.py) still computes on the GPU."""
+    torch.manual_seed(0)
+    n = svb.SpeechEmbedder()
+    assert list(n.state_dict().keys()) == oemb.PARAM_NAMES
+    x = torch.tensor(I.logmel(5, 30, seed=3))
+    with torch.no_grad():
+        e_cpu_module = n(x)
+        e_gpu_module = svb.SpeechEmbedder().cuda()
+        e_gpu_module.load_state_dict(n.state_dict())
+        e2 = e_gpu_module(x.cuda()).cpu()
+    assert e_cpu_module.device.type == "cpu"
+    assert torch.equal(e_cpu_module, e2)
