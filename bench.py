@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""Benchmark of the GE2E training hot path (BASELINE.json metric: train utts/sec, LSTM+GE2E fwd+bwd, N=64 M=10).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Workload = BASELINE.json configs[1]: 64 speakers x 10 utterances x 160 frames x
+40 mel per GPU, synthetic log-mel, reference-initialised weights.  Under torchrun (N > 1) every rank owns 64
+speakers (weak scaling), d-vectors are all-gathered for the global GE2E batch (configs[2] at N=8) and parameter
+gradients are all-reduced (SUM).
+
+  value : utterances/s of fwd + GE2E + bwd with the batch already resident in HBM
+  e2e   : the caller's whole step through the public API -- H2D of the pinned host batch, zero_grad, forward, GE2E,
+          backward, the two clip_grad_norm_ and the SGD step of train_speech_embedder.py:54-65, D2H of the loss
+  --impl reference : the reference's CPU path (oracle port calling the same torch CPU library entry points the
+          reference calls), all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_SPK, M_UTT, T_FR, NMELS, HID, NLAYER, PROJ = 64, 10, 160, 40, 768, 3, 256
+METRIC = "train utts/sec (LSTM+GE2E fwd+bwd, N=64 M=10)"
+PHASES = ["prep", "input_gemm", "recurrent_fwd", "projection", "projection_bwd", "recurrent_bwd", "weight_grads",
+          "bias_grads", "dx"]
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def launches_per_step(world):
+    fwd = 1 + NLAYER * (1 + T_FR) + 1                 # prep, per layer input GEMM + T fused step kernels, projection
+    loss = 1                                           # fused GE2E (cooperative)
+    bwd = 1 + 4 + NLAYER * (T_FR + 2 + 2) + (NLAYER - 1)   # scale3, projection bwd, per layer BPTT + 2 wgrad + 2 bias, dX
+    pack = NLAYER                                      # bf16 shadow refresh after the optimizer step
+    return fwd + loss + bwd + pack
+
+
+def cpu_reference_rate(steps, warmup, budget_s=150.0):
+    """Reference CPU path on all host threads over a bounded sample; returns (utts/s, description, cores)."""
+    import torch
+    import _inputs as I
+    from oracle.embedder import ReferenceLibraryStep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # probe with 1 speaker-group of 4 x 10 utterances to size the sample
+    probe = ReferenceLibraryStep(4, M_UTT)
+    xb = torch.tensor(I.logmel(4 * M_UTT, T_FR, seed=1234))
+    probe.step(xb)
+    t0 = time.perf_counter()
+    probe.step(xb)
+    per_utt = (time.perf_counter() - t0) / (4 * M_UTT)
+    n = N_SPK
+    while n > 4 and per_utt * n * M_UTT * (steps + warmup) > budget_s:
+        n //= 2
+    ref = ReferenceLibraryStep(n, M_UTT)
+    xb = torch.tensor(I.logmel(n * M_UTT, T_FR, seed=1234))
+    for _ in range(warmup):
+        ref.step(xb)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ref.step(xb)
+        ts.append(time.perf_counter() - t0)
+    dt = statistics.median(ts)
+    sample = (f"{n} speakers x {M_UTT} utts x {T_FR} frames per step (of the 64 x 10 workload), full train step "
+              f"(fwd+GE2E+bwd+clip+SGD, train_speech_embedder.py:54-65), {steps} steps after {warmup} warm-up, median")
+    return n * M_UTT / dt, sample, cores, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    rate, sample, cores, dt = cpu_reference_rate(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "utts/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "GE2E train step N=64 x M=10, 160 frames x 40 mel (BASELINE configs[1])",
+                       "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recurrent-terms", type=int, default=1)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import _inputs as I
+    import pytorch_speaker_verification_b200 as svb
+    from pytorch_speaker_verification_b200 import _lib
+    from pytorch_speaker_verification_b200.dist import GlobalGE2ELoss, allreduce_gradients
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    torch.manual_seed(0)                                   # same init on every rank (reference init order)
+    net = svb.SpeechEmbedder().to(dev)
+    net.recurrent_terms = args.recurrent_terms
+    crit = svb.GE2ELoss(dev)
+    loss_mod = GlobalGE2ELoss(crit) if world > 1 else crit
+    params = list(net.parameters())
+    opt = torch.optim.SGD([{'params': net.parameters()}, {'params': crit.parameters()}], lr=0.01)
+    B = N_SPK * M_UTT
+    x_host = torch.tensor(I.logmel(B, T_FR, seed=1234 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def fwd_bwd(x):
+        emb = net(x)
+        loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(params)
+        return loss
+
+    def full_step():
+        x = x_host.to(dev, non_blocking=True)
+        opt.zero_grad()
+        loss = fwd_bwd(x)
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 3.0)
+        torch.nn.utils.clip_grad_norm_(crit.parameters(), 1.0)
+        opt.step()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in evs:
+            flush.zero_()                                   # L2 flush between timed iterations (untimed)
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+
+    def phase_profile(fn, steps=3):
+        """Per-phase device time (CUDA events recorded by the library on the launching stream), averaged."""
+        acc = [0.0] * len(PHASES)
+        buf = (ctypes.c_float * 16)()
+        for _ in range(steps):
+            flush.zero_()
+            L.svb_profile_enable(1)
+            fn()
+            torch.cuda.synchronize()
+            L.svb_profile_read(buf, 16)
+            for i in range(len(PHASES)):
+                acc[i] += buf[i]
+        L.svb_profile_enable(0)
+        return {n: acc[i] / steps for i, n in enumerate(PHASES)}
+
+    def value_step():
+        for p in list(params) + [crit.w, crit.b]:
+            p.grad = None
+        return fwd_bwd(x_dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_value = timed(value_step, args.steps, args.warmup)
+    ms_e2e = timed(full_step, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    phases = phase_profile(value_step) if rank == 0 else None
+    barrier()
+    loss_val = float(loss_host)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        utts = B * world
+        # roofline of the dominant kernel class
+        flops_step = 2.0 * B * 4 * HID * HID               # one recurrent frame: (B x H) . (H x 4H), fwd == bwd
+        dom = max(("recurrent_fwd", "recurrent_bwd", "input_gemm", "weight_grads"), key=lambda k: phases[k])
+        if dom in ("recurrent_fwd", "recurrent_bwd"):
+            launches = NLAYER * T_FR
+            flops_launch = flops_step * args.recurrent_terms if dom == "recurrent_fwd" else flops_step
+            kern = "tc_gemm_kernel<EpiLstmFwd>" if dom == "recurrent_fwd" else "tc_gemm_kernel<EpiLstmBwd>"
+        elif dom == "input_gemm":
+            launches = NLAYER
+            flops_launch = 2.0 * B * T_FR * 4 * HID * (NMELS + 2 * HID) / 3 * 3   # 3 split-bf16 terms (averaged/layer)
+            kern = "tc_gemm_kernel<EpiStoreF32> (input projection)"
+        else:
+            launches = 2 * NLAYER
+            flops_launch = 2.0 * B * T_FR * 4 * HID * (NMELS + 5 * HID) / 6
+            kern = "tc_gemm_kernel<EpiStoreF32, MN-major> (weight gradients)"
+        avg_ms = phases[dom] / launches
+        achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        line = {
+            "metric": METRIC, "value": utts / (ms_value * 1e-3), "unit": "utts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "GE2E train step, 64 speakers x 10 utts x 160 frames x 40 mel per GPU "
+                                   "(BASELINE configs[1]; global batch = 64 x n_gpus speakers, configs[2] at 8)",
+                       "model": "3-layer LSTM 40->768, Linear 768->256, L2 norm; GE2E w=10 b=-5; reference init seed 0",
+                       "precision": f"input projection split-bf16 x3, recurrent bf16 x{args.recurrent_terms}, "
+                                    "fp32 accumulate/gates/loss",
+                       "parallelism": f"dp{world} by speaker group" if world > 1 else "single GPU",
+                       "l2": "192 MiB buffer written between timed iterations (untimed)",
+                       "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
+            "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utts/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step(world) * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": f"{pk_src} (sustained bf16)",
+                         "avg_launch_us": avg_ms * 1e3, "launches_per_step": launches,
+                         # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)
+                         "whole_step_frac": 11443765248.0 * B / 1e12 / (ms_value * 1e-3) / peak},
+            "phases_ms": phases,
+            "loss": loss_val,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sample, cores, _ = cpu_reference_rate(2, 1, budget_s=40.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,17 @@ int svb_embedder_forward(const void* x, int x_dtype, const void* packed, const f
 int svb_embedder_backward(const float* demb, const void* packed, const float* proj_w, float* const* grads,
                           void* workspace, int B, int T, int I, int H, int L, int P, void* stream);
 
+/* Recurrent forward kernel selection: 0 (default) = one fused GEMM+cell launch per frame (TMA-staged epilogue);
+ * 1 = experimental persistent cooperative kernel (W_hh resident in shared memory, h staged through tensor memory,
+ * per-batch-tile frame counters) when H is 256/512/768 and rec_terms == 1. */
+int svb_set_persistent(int on);
+
+/* Optional phase timing (CUDA events around the phases of forward/backward; none inside the per-frame loops).
+ * Phases: 0 prep, 1 input GEMM, 2 recurrent fwd, 3 projection, 4 projection bwd, 5 recurrent bwd, 6 weight grads,
+ * 7 bias grads, 8 dX.  svb_profile_read sums elapsed ms per phase since the last enable/read (sync the stream first). */
+int svb_profile_enable(int on);
+int svb_profile_read(float* ms_per_phase, int nphases);
+
 /* ---- GE2E loss (speech_embedder_net.py:35-49, utils.py:27-132) ---------------------------------------------------- */
 
 int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);

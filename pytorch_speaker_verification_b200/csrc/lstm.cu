@@ -31,6 +31,7 @@ static inline int round8(int x) { return (x + 7) & ~7; }
 struct LayerW {
   __nv_bfloat16 *wih_hi, *wih_lo;   // [4H, Ip] packed rows
   __nv_bfloat16 *whh_hi, *whh_lo;   // [4H, H]  packed rows
+  __nv_bfloat16 *whhT;              // [H, 4H]  transpose of whh_hi (B operand of the BPTT frame GEMM)
   float* bias;                      // [4H] packed, b_ih + b_hh
   int I, Ip;
 };
@@ -49,6 +50,7 @@ static PackedW layout_packed(char* base, int I, int H, int L) {
     pw.l[l].wih_lo = (__nv_bfloat16*)take((size_t)4 * H * Ip * 2);
     pw.l[l].whh_hi = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
     pw.l[l].whh_lo = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
+    pw.l[l].whhT = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
     pw.l[l].bias = (float*)take((size_t)4 * H * 4);
   }
   pw.bytes = off;
@@ -71,6 +73,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     lw.whh_hi[(size_t)p * H + k] = hi;
     lw.whh_lo[(size_t)p * H + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    lw.whhT[(size_t)k * 4 * H + p] = hi;
   }
   if (threadIdx.x == 0) lw.bias[p] = b_ih[r] + b_hh[r];
 }
@@ -86,6 +89,7 @@ struct Work {
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
   float *dh_above, *dc, *dh_last, *dy;  // backward: [T,B,H], [B,H], [B,H], [B,P]
   float* colsum_part;               // [chunks, 4H]
+  unsigned* counters;               // [L][64] frame counters of the persistent kernel
   int cslots;
   size_t bytes;
 };
@@ -108,6 +112,7 @@ static Work layout_work(char* base, const Dims& d, int training) {
   w.h_last = (float*)take(B * H * 4);
   w.y = (float*)take(B * d.P * 4);
   w.inv_norm = (float*)take(B * 4);
+  w.counters = (unsigned*)take(8 * 64 * 4);
   if (training) {
     w.dh_above = (float*)take(T * B * H * 4);
     w.dc = (float*)take(B * H * 4);
@@ -143,8 +148,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float bf16_lo_of(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi_of(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// Forward cell: acc = W_hh h_{t-1} for 8 units x 4 gates (packed chunk); adds gin, applies the gates.
-struct EpiLstmFwd {
+// ---- cell math shared by every forward kernel: 8 units, gates i|f|g|o in pre[0..8) [8..16) [16..24) [24..32)
+struct CellRegs { float cn[8], hn[8], gi[8], gf[8], gg[8], go[8]; };
+__device__ __forceinline__ void lstm_cell8(const float (&pre)[32], const float (&cp)[8], CellRegs& r) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    r.gi[j] = sigmoidf_fast(pre[j]);
+    r.gf[j] = sigmoidf_fast(pre[8 + j]);
+    r.gg[j] = tanhf_fast(pre[16 + j]);
+    r.go[j] = sigmoidf_fast(pre[24 + j]);
+    r.cn[j] = r.gf[j] * cp[j] + r.gi[j] * r.gg[j];
+    r.hn[j] = r.go[j] * tanhf_fast(r.cn[j]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void split_h8(const float (&hn)[8], uint4& hi, uint4& lo) {
+  uint32_t hh[4], hl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hh[j] = pack_bf16x2(hn[2 * j], hn[2 * j + 1]);
+    hl[j] = pack_bf16x2(hn[2 * j] - bf16_lo_of(hh[j]), hn[2 * j + 1] - bf16_hi_of(hh[j]));
+  }
+  hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+  lo = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+}
+
+// Pointer-based cell (direct global stores); used by the persistent kernel in plstm.cuh.
+struct CellDirect {
   struct Params {
     const float* gin;          // [B, 4H] slice of step t
     const float* c_prev;       // [B, H]
@@ -155,137 +187,177 @@ struct EpiLstmFwd {
     float* h_f32;              // [B, H], nullable (top layer, last step)
     int H;
   };
-  struct Tile {};
-  static __device__ __forceinline__ void prologue(const Params& p, Tile&, int m, int n0, bool valid) {
-    if (valid) {
-      const float* g = p.gin + (size_t)m * 4 * p.H + n0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 32));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 64));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 96));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.c_prev + (size_t)m * p.H + (n0 >> 2)));
-    }
-  }
-  static __device__ __forceinline__ void apply(const Params& p, Tile&, int m, int n0, float (&acc)[32]) {
+  static __device__ __forceinline__ void cell(const Params& p, int m, int n0, const float (&pre)[32], const float (&cp)[8]) {
     const int u0 = (n0 >> 5) * 8;
-    const float4* g4 = reinterpret_cast<const float4*>(p.gin + (size_t)m * 4 * p.H + n0);
-    float pre[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 v = __ldg(g4 + j);
-      pre[4 * j + 0] = acc[4 * j + 0] + v.x; pre[4 * j + 1] = acc[4 * j + 1] + v.y;
-      pre[4 * j + 2] = acc[4 * j + 2] + v.z; pre[4 * j + 3] = acc[4 * j + 3] + v.w;
-    }
     const size_t hoff = (size_t)m * p.H + u0;
-    const float4 c0 = *reinterpret_cast<const float4*>(p.c_prev + hoff);
-    const float4 c1 = *reinterpret_cast<const float4*>(p.c_prev + hoff + 4);
-    const float cp[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    float cn[8], hn[8], gi[8], gf[8], gg[8], go[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      gi[j] = sigmoidf_fast(pre[j]);
-      gf[j] = sigmoidf_fast(pre[8 + j]);
-      gg[j] = tanhf_fast(pre[16 + j]);
-      go[j] = sigmoidf_fast(pre[24 + j]);
-      cn[j] = gf[j] * cp[j] + gi[j] * gg[j];
-      hn[j] = go[j] * tanhf_fast(cn[j]);
-    }
-    *reinterpret_cast<float4*>(p.c_out + hoff) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-    *reinterpret_cast<float4*>(p.c_out + hoff + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-    uint32_t hh[4], hl[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hh[j] = pack_bf16x2(hn[2 * j], hn[2 * j + 1]);
-      hl[j] = pack_bf16x2(hn[2 * j] - bf16_lo_of(hh[j]), hn[2 * j + 1] - bf16_hi_of(hh[j]));
-    }
-    *reinterpret_cast<uint4*>(p.h_hi + hoff) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    if (p.h_lo) *reinterpret_cast<uint4*>(p.h_lo + hoff) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+    CellRegs r;
+    lstm_cell8(pre, cp, r);
+    *reinterpret_cast<float4*>(p.c_out + hoff) = make_float4(r.cn[0], r.cn[1], r.cn[2], r.cn[3]);
+    *reinterpret_cast<float4*>(p.c_out + hoff + 4) = make_float4(r.cn[4], r.cn[5], r.cn[6], r.cn[7]);
+    uint4 hi, lo;
+    split_h8(r.hn, hi, lo);
+    *reinterpret_cast<uint4*>(p.h_hi + hoff) = hi;
+    if (p.h_lo) *reinterpret_cast<uint4*>(p.h_lo + hoff) = lo;
     if (p.h_f32) {
-      *reinterpret_cast<float4*>(p.h_f32 + hoff) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-      *reinterpret_cast<float4*>(p.h_f32 + hoff + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      *reinterpret_cast<float4*>(p.h_f32 + hoff) = make_float4(r.hn[0], r.hn[1], r.hn[2], r.hn[3]);
+      *reinterpret_cast<float4*>(p.h_f32 + hoff + 4) = make_float4(r.hn[4], r.hn[5], r.hn[6], r.hn[7]);
     }
     if (p.gates) {
       uint4* go4 = reinterpret_cast<uint4*>(p.gates + (size_t)m * 4 * p.H + n0);
-      go4[0] = make_uint4(pack_bf16x2(gi[0], gi[1]), pack_bf16x2(gi[2], gi[3]), pack_bf16x2(gi[4], gi[5]), pack_bf16x2(gi[6], gi[7]));
-      go4[1] = make_uint4(pack_bf16x2(gf[0], gf[1]), pack_bf16x2(gf[2], gf[3]), pack_bf16x2(gf[4], gf[5]), pack_bf16x2(gf[6], gf[7]));
-      go4[2] = make_uint4(pack_bf16x2(gg[0], gg[1]), pack_bf16x2(gg[2], gg[3]), pack_bf16x2(gg[4], gg[5]), pack_bf16x2(gg[6], gg[7]));
-      go4[3] = make_uint4(pack_bf16x2(go[0], go[1]), pack_bf16x2(go[2], go[3]), pack_bf16x2(go[4], go[5]), pack_bf16x2(go[6], go[7]));
+      go4[0] = pack8(r.gi); go4[1] = pack8(r.gf); go4[2] = pack8(r.gg); go4[3] = pack8(r.go);
     }
   }
 };
 
-// Backward cell: acc = dG_{t+1} W_hh (recurrent part of dL/dh_t) for 32 hidden units of one batch row.
-struct EpiLstmBwd {
-  struct Params {
-    __nv_bfloat16* gates;      // [B, 4H] slice of step t: activations in, dG out (in place)
-    const float* c_t;          // [B, H]
-    const float* c_prev;       // [B, H]
-    float* dc;                 // [B, H] running dL/dc (in place)
-    const float* dh_above;     // [B, H] gradient from the layer above at step t, nullable
-    int H;
-    int use_acc;               // 0 at t = T-1 (no recurrent contribution yet)
+// Forward frame epilogue (BN = 128 packed gate columns = 32 units): acc = W_hh h_{t-1}.
+// TMA-loaded inputs (swizzled smem): gin tile 4 x [128 rows x 32 fp32], c_{t-1} tile [128 x 32 fp32].
+// TMA-stored outputs (staging): c_t [128 x 32 fp32], h_t hi/lo [128 x 32 bf16], gates 2 x [128 x 64 bf16].
+struct EpiLstmFwd {
+  struct __align__(64) Params {
+    CUtensorMap t_gin;     // fp32 (4H, B, T)       box {32,128} SW128   load
+    CUtensorMap t_c;       // fp32 (H, B, cslots)   box {32,128} SW128   load + store
+    CUtensorMap t_hhi;     // bf16 (H, B, T+1)      box {32,128} no swizzle   store
+    CUtensorMap t_hlo;     // same, lo part
+    CUtensorMap t_gates;   // bf16 (4H, B, T+1)     box {64,128} SW128   store
+    float* h_f32;          // [B, H] or null: fp32 copy of h_t (top layer, last frame), direct stores
+    int t, c_prev_slot, c_out_slot, has_hlo, has_gates, H;
   };
-  struct Tile {};
-  static __device__ __forceinline__ void prologue(const Params& p, Tile&, int m, int n0, bool valid) {
-    if (valid) {
-      const __nv_bfloat16* g = p.gates + (size_t)m * 4 * p.H + 4 * n0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 64));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.c_t + (size_t)m * p.H + n0));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.c_prev + (size_t)m * p.H + n0));
+  static constexpr int kGin = 0, kCprev = 65536;
+  static constexpr int kInBytes = 65536 + 16384;
+  static constexpr int kOc = 0, kOhi = 16384, kOlo = 24576, kOg = 32768;
+  static constexpr int kOutBytes = 65536;
+  static __device__ __forceinline__ void issue_loads(const Params& p, uint8_t* in, uint64_t* bar, int m0, int n0) {
+    mbar_expect_tx(bar, kInBytes);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tma_load_3d(in + kGin + c * 16384, &p.t_gin, bar, n0 + 32 * c, m0, p.t);
+    tma_load_3d(in + kCprev, &p.t_c, bar, n0 >> 2, m0, p.c_prev_slot);
+  }
+  static __device__ __forceinline__ void apply(const Params& p, const uint8_t* in, uint8_t* out, int row, int m, int n0,
+                                               int c, float (&acc)[32], bool valid) {
+    float pre[32], cp[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(in + kGin + c * 16384 + sw128(row, j));
+      pre[4 * j + 0] = acc[4 * j + 0] + v.x; pre[4 * j + 1] = acc[4 * j + 1] + v.y;
+      pre[4 * j + 2] = acc[4 * j + 2] + v.z; pre[4 * j + 3] = acc[4 * j + 3] + v.w;
+    }
+    {
+      const float4 a = *reinterpret_cast<const float4*>(in + kCprev + sw128(row, 2 * c));
+      const float4 b = *reinterpret_cast<const float4*>(in + kCprev + sw128(row, 2 * c + 1));
+      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
+    }
+    CellRegs r;
+    lstm_cell8(pre, cp, r);
+    *reinterpret_cast<float4*>(out + kOc + sw128(row, 2 * c)) = make_float4(r.cn[0], r.cn[1], r.cn[2], r.cn[3]);
+    *reinterpret_cast<float4*>(out + kOc + sw128(row, 2 * c + 1)) = make_float4(r.cn[4], r.cn[5], r.cn[6], r.cn[7]);
+    uint4 hi, lo;
+    split_h8(r.hn, hi, lo);
+    *reinterpret_cast<uint4*>(out + kOhi + row * 64 + c * 16) = hi;
+    *reinterpret_cast<uint4*>(out + kOlo + row * 64 + c * 16) = lo;
+    uint8_t* og = out + kOg + (c >> 1) * 16384;
+    const int ub = (c & 1) * 4;
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8(r.gi);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8(r.gf);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8(r.gg);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8(r.go);
+    if (p.h_f32 && valid) {
+      float* d = p.h_f32 + (size_t)m * p.H + (n0 >> 2) + 8 * c;
+      *reinterpret_cast<float4*>(d) = make_float4(r.hn[0], r.hn[1], r.hn[2], r.hn[3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(r.hn[4], r.hn[5], r.hn[6], r.hn[7]);
     }
   }
-  static __device__ __forceinline__ void apply(const Params& p, Tile&, int m, int n0, float (&acc)[32]) {
-    // n0 = first hidden unit of the chunk (multiple of 32) -> packed columns [4 n0, 4 n0 + 128)
+  static __device__ __forceinline__ void issue_stores(const Params& p, const uint8_t* out, int m0, int n0) {
+    tma_store_3d(&p.t_c, out + kOc, n0 >> 2, m0, p.c_out_slot);
+    tma_store_3d(&p.t_hhi, out + kOhi, n0 >> 2, m0, p.t + 1);
+    if (p.has_hlo) tma_store_3d(&p.t_hlo, out + kOlo, n0 >> 2, m0, p.t + 1);
+    if (p.has_gates) {
+      tma_store_3d(&p.t_gates, out + kOg, n0, m0, p.t);
+      tma_store_3d(&p.t_gates, out + kOg + 16384, n0 + 64, m0, p.t);
+    }
+  }
+};
+
+// Backward frame epilogue (BN = 32 hidden units): acc = dG_{t+1} W_hh, the recurrent part of dL/dh_t.
+// TMA-loaded inputs: gate activations 2 x [128 x 64 bf16], c_t, c_{t-1}, running dL/dc, dL/dh from above
+// (each [128 x 32 fp32]).  TMA-stored outputs: dG (in place of the activations) and the updated dL/dc.
+struct EpiLstmBwd {
+  struct __align__(64) Params {
+    CUtensorMap t_gates;   // bf16 (4H, B, T+1)  box {64,128} SW128   load + store (in place)
+    CUtensorMap t_c;       // fp32 (H, B, T+1)   box {32,128} SW128   load
+    CUtensorMap t_dc;      // fp32 (H, B, 1)     box {32,128} SW128   load + store
+    CUtensorMap t_dha;     // fp32 (H, B, slots) box {32,128} SW128   load (optional)
+    int t, has_dha, dha_slot;
+  };
+  static constexpr int kG = 0, kCt = 32768, kCp = 49152, kDc = 65536, kDha = 81920;
+  static constexpr int kInBytes = 98304;
+  static constexpr int kOg = 0, kOdc = 32768;
+  static constexpr int kOutBytes = 49152;
+  static __device__ __forceinline__ void issue_loads(const Params& p, uint8_t* in, uint64_t* bar, int m0, int n0) {
+    mbar_expect_tx(bar, p.has_dha ? kInBytes : kInBytes - 16384);
+    tma_load_3d(in + kG, &p.t_gates, bar, 4 * n0, m0, p.t);
+    tma_load_3d(in + kG + 16384, &p.t_gates, bar, 4 * n0 + 64, m0, p.t);
+    tma_load_3d(in + kCt, &p.t_c, bar, n0, m0, p.t + 1);
+    tma_load_3d(in + kCp, &p.t_c, bar, n0, m0, p.t);
+    tma_load_3d(in + kDc, &p.t_dc, bar, n0, m0, 0);
+    if (p.has_dha) tma_load_3d(in + kDha, &p.t_dha, bar, n0, m0, p.dha_slot);
+  }
+  static __device__ __forceinline__ void ld8(const uint8_t* base, int row, int u, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(base + sw128(row, u));
+    const float4 b = *reinterpret_cast<const float4*>(base + sw128(row, u + 1));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void unpack8(uint4 w, float (&v)[8]) {
+    v[0] = bf16_lo_of(w.x); v[1] = bf16_hi_of(w.x); v[2] = bf16_lo_of(w.y); v[3] = bf16_hi_of(w.y);
+    v[4] = bf16_lo_of(w.z); v[5] = bf16_hi_of(w.z); v[6] = bf16_lo_of(w.w); v[7] = bf16_hi_of(w.w);
+  }
+  static __device__ __forceinline__ void apply(const Params& p, const uint8_t* in, uint8_t* out, int row, int, int,
+                                               int, float (&acc)[32], bool) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const size_t hoff = (size_t)m * p.H + n0 + 8 * q;
-      uint4* gp = reinterpret_cast<uint4*>(p.gates + (size_t)m * 4 * p.H + 4 * n0 + 32 * q);
-      const uint4 vi = gp[0], vf = gp[1], vg = gp[2], vo = gp[3];
-      const uint32_t wi[4] = {vi.x, vi.y, vi.z, vi.w}, wf[4] = {vf.x, vf.y, vf.z, vf.w};
-      const uint32_t wg[4] = {vg.x, vg.y, vg.z, vg.w}, wo[4] = {vo.x, vo.y, vo.z, vo.w};
-      float ct[8], cp[8], dcs[8], dha[8];
-      {
-        const float4 a0 = *reinterpret_cast<const float4*>(p.c_t + hoff), a1 = *reinterpret_cast<const float4*>(p.c_t + hoff + 4);
-        ct[0] = a0.x; ct[1] = a0.y; ct[2] = a0.z; ct[3] = a0.w; ct[4] = a1.x; ct[5] = a1.y; ct[6] = a1.z; ct[7] = a1.w;
-        const float4 b0 = *reinterpret_cast<const float4*>(p.c_prev + hoff), b1 = *reinterpret_cast<const float4*>(p.c_prev + hoff + 4);
-        cp[0] = b0.x; cp[1] = b0.y; cp[2] = b0.z; cp[3] = b0.w; cp[4] = b1.x; cp[5] = b1.y; cp[6] = b1.z; cp[7] = b1.w;
-        const float4 d0 = *reinterpret_cast<const float4*>(p.dc + hoff), d1 = *reinterpret_cast<const float4*>(p.dc + hoff + 4);
-        dcs[0] = d0.x; dcs[1] = d0.y; dcs[2] = d0.z; dcs[3] = d0.w; dcs[4] = d1.x; dcs[5] = d1.y; dcs[6] = d1.z; dcs[7] = d1.w;
-        if (p.dh_above) {
-          const float4 e0 = *reinterpret_cast<const float4*>(p.dh_above + hoff), e1 = *reinterpret_cast<const float4*>(p.dh_above + hoff + 4);
-          dha[0] = e0.x; dha[1] = e0.y; dha[2] = e0.z; dha[3] = e0.w; dha[4] = e1.x; dha[5] = e1.y; dha[6] = e1.z; dha[7] = e1.w;
-        } else {
+    for (int q = 0; q < 4; ++q) {                       // 8 units each
+      const uint8_t* gb = in + kG + (q >> 1) * 16384;
+      const int ub = (q & 1) * 4;
+      float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dcs[8], dha[8];
+      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 0)), gi);
+      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 1)), gf);
+      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 2)), gg);
+      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 3)), go);
+      ld8(in + kCt, row, 2 * q, ct);
+      ld8(in + kCp, row, 2 * q, cp);
+      ld8(in + kDc, row, 2 * q, dcs);
+      if (p.has_dha) ld8(in + kDha, row, 2 * q, dha);
+      else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dha[j] = 0.f;
-        }
+        for (int j = 0; j < 8; ++j) dha[j] = 0.f;
       }
       float di[8], df[8], dg[8], dO[8], dcn[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t si = wi[j >> 1], sf = wf[j >> 1], sg = wg[j >> 1], so = wo[j >> 1];
-        const float gi = (j & 1) ? bf16_hi_of(si) : bf16_lo_of(si);
-        const float gf = (j & 1) ? bf16_hi_of(sf) : bf16_lo_of(sf);
-        const float gg = (j & 1) ? bf16_hi_of(sg) : bf16_lo_of(sg);
-        const float go = (j & 1) ? bf16_hi_of(so) : bf16_lo_of(so);
-        const float dh = (p.use_acc ? acc[8 * q + j] : 0.f) + dha[j];
+        const float dh = acc[8 * q + j] + dha[j];
         const float tc = tanhf_fast(ct[j]);
-        const float dc = dh * go * (1.f - tc * tc) + dcs[j];
-        dO[j] = dh * tc * go * (1.f - go);
-        di[j] = dc * gg * gi * (1.f - gi);
-        df[j] = dc * cp[j] * gf * (1.f - gf);
-        dg[j] = dc * gi * (1.f - gg * gg);
-        dcn[j] = dc * gf;
+        const float dc = dh * go[j] * (1.f - tc * tc) + dcs[j];
+        dO[j] = dh * tc * go[j] * (1.f - go[j]);
+        di[j] = dc * gg[j] * gi[j] * (1.f - gi[j]);
+        df[j] = dc * cp[j] * gf[j] * (1.f - gf[j]);
+        dg[j] = dc * gi[j] * (1.f - gg[j] * gg[j]);
+        dcn[j] = dc * gf[j];
       }
-      *reinterpret_cast<float4*>(p.dc + hoff) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-      *reinterpret_cast<float4*>(p.dc + hoff + 4) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
-      gp[0] = make_uint4(pack_bf16x2(di[0], di[1]), pack_bf16x2(di[2], di[3]), pack_bf16x2(di[4], di[5]), pack_bf16x2(di[6], di[7]));
-      gp[1] = make_uint4(pack_bf16x2(df[0], df[1]), pack_bf16x2(df[2], df[3]), pack_bf16x2(df[4], df[5]), pack_bf16x2(df[6], df[7]));
-      gp[2] = make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]), pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7]));
-      gp[3] = make_uint4(pack_bf16x2(dO[0], dO[1]), pack_bf16x2(dO[2], dO[3]), pack_bf16x2(dO[4], dO[5]), pack_bf16x2(dO[6], dO[7]));
+      uint8_t* og = out + kOg + (q >> 1) * 16384;
+      *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8(di);
+      *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8(df);
+      *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8(dg);
+      *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8(dO);
+      *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+      *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q + 1)) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
     }
   }
+  static __device__ __forceinline__ void issue_stores(const Params& p, const uint8_t* out, int m0, int n0) {
+    tma_store_3d(&p.t_gates, out + kOg, 4 * n0, m0, p.t);
+    tma_store_3d(&p.t_gates, out + kOg + 16384, 4 * n0 + 64, m0, p.t);
+    tma_store_3d(&p.t_dc, out + kOdc, n0, m0, 0);
+  }
 };
+
+#include "plstm.cuh"
 
 // ------------------------------------------------------------------------------------------ projection + L2 norm
 // y[b,:] = W h_last[b,:] + bias; emb = y/|y|   (speech_embedder_net.py:31-32; fp32; 8 batch rows per CTA)
@@ -422,6 +494,27 @@ __global__ void bias_grad_finish_kernel(const float* __restrict__ part, int chun
   g_hh[r] = acc;
 }
 
+// ------------------------------------------------------------------------------------------ phase profiler
+// Optional CUDA-event brackets around the phases of forward/backward (a handful of events per call, none inside
+// the per-frame loops), read back by bench.py for the per-kernel roofline.
+enum Phase { PH_PREP = 0, PH_IN_GEMM, PH_REC_FWD, PH_PROJ, PH_PROJ_BWD, PH_REC_BWD, PH_WGRAD, PH_BIAS, PH_DX, PH_COUNT };
+struct Profiler {
+  bool on = false;
+  int n = 0;
+  cudaEvent_t ev[256];
+  int phase[256];
+  int created = 0;
+};
+static Profiler g_prof;
+static int g_persistent = 0;
+static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
+  if (!g_prof.on || g_prof.n >= 256) return;
+  if (g_prof.n >= g_prof.created) { cudaEventCreate(&g_prof.ev[g_prof.created]); g_prof.created++; }
+  cudaEventRecord(g_prof.ev[g_prof.n], s);
+  g_prof.phase[g_prof.n] = phase;
+  g_prof.n++;
+}
+
 // ------------------------------------------------------------------------------------------ drivers
 #define SVB_TRY(expr) do { int _e = (expr); if (_e != SVB_OK) return _e; } while (0)
 #define SVB_CUDA(what) do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { set_error(what, _e); return SVB_ERR_CUDA; } } while (0)
@@ -432,15 +525,32 @@ static int check_dims(const Dims& d) {
   return SVB_OK;
 }
 
-template <class Epi, int BN, bool B_MN>
+template <class Epi, int BN, int kStages, bool B_MN>
 static int launch_step(GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t s) {
-  cudaError_t e = launch_tc_gemm<BN, 4, false, B_MN, Epi>(ops, ep, s);
+  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi>(ops, ep, s);
   if (e != cudaSuccess) { set_error("lstm step launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }
 
 }  // namespace svb
 using namespace svb;
+
+// 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
+extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
+extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
+// Sums the elapsed ms per phase since the last enable/read; the caller must have synchronised the stream.
+extern "C" int svb_profile_read(float* ms_per_phase, int nphases) {
+  if (!ms_per_phase || nphases < PH_COUNT) return SVB_ERR_ARG;
+  for (int i = 0; i < nphases; ++i) ms_per_phase[i] = 0.f;
+  for (int i = 0; i + 1 < g_prof.n; ++i) {
+    if (g_prof.phase[i] < 0) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]) != cudaSuccess) return SVB_ERR_CUDA;
+    ms_per_phase[g_prof.phase[i]] += ms;
+  }
+  g_prof.n = 0;
+  return SVB_OK;
+}
 
 extern "C" int svb_embedder_sizes(int B, int T, int I, int H, int L, int P, int training, size_t* packed_bytes,
                                   size_t* workspace_bytes) {
@@ -475,6 +585,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
   Work w = layout_work(static_cast<char*>(workspace), d, training);
   const int Ip0 = round8(I);
   const size_t BH = (size_t)B * H;
+  prof_mark(PH_PREP, s);
   {
     const size_t n = (size_t)T * B * Ip0;
     const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
@@ -492,6 +603,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
   for (int l = 0; l < L; ++l) {
     const LayerW& lw = pw.l[l];
     // ---- input projection over all frames: gin[T*B, 4H] = X W_ih^T + bias (3-term split bf16)
+    prof_mark(PH_IN_GEMM, s);
     {
       const __nv_bfloat16* xh = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;   // slots 1..T of the layer below
       const __nv_bfloat16* xl = l == 0 ? w.x_lo : w.h_lo[l - 1] + BH;
@@ -504,11 +616,40 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
         SVB_TRY(make_operand_map(&ops.ta[t], As[t], T * B, lw.Ip, lw.Ip, 0, kBM));
         SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 128));
       }
-      EpiStoreF32::Params ep{w.gin, lw.bias, (int64_t)4 * H, 4 * H, 0};
-      cudaError_t e = launch_tc_gemm<128, 4, false, false, EpiStoreF32>(ops, ep, s);
+      EpiStoreF32<128>::Params ep;
+      SVB_TRY(make_store_params<128>(&ep, w.gin, lw.bias, T * B, 4 * H, (int64_t)4 * H, 0));
+      cudaError_t e = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>>(ops, ep, s);
       if (e != cudaSuccess) { set_error("input projection", e); return SVB_ERR_CUDA; }
     }
-    // ---- recurrence: one fused GEMM + cell kernel per frame
+    prof_mark(PH_REC_FWD, s);
+    // ---- recurrence, persistent form: one cooperative launch per (layer, <=6 batch tiles) runs all T frames
+    if (g_persistent && rec_terms == 1 && (H == 768 || H == 512 || H == 256)) {
+      static int num_sms = 0;
+      if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int max_tiles = num_sms / (H / 32) < 64 ? num_sms / (H / 32) : 64;
+      if (max_tiles >= 1) {
+        PlstmParams pp;
+        memset(&pp, 0, sizeof(pp));
+        SVB_TRY(make_operand_map(&pp.tw, lw.whh_hi, 4 * H, H, H, 0, 128));
+        pp.h_hi = w.h_hi[l]; pp.h_hi_w = w.h_hi[l];
+        pp.h_lo = (l + 1 < L) ? w.h_lo[l] : nullptr;
+        pp.gin = w.gin; pp.c = w.c[l]; pp.gates = training ? w.gates[l] : nullptr;
+        pp.h_last = (l == L - 1) ? w.h_last : nullptr;
+        pp.B = B; pp.T = T; pp.training = training;
+        const int tiles = (B + kBM - 1) / kBM;
+        for (int tile0 = 0; tile0 < tiles; tile0 += max_tiles) {
+          const int nt = tiles - tile0 < max_tiles ? tiles - tile0 : max_tiles;
+          pp.counters = w.counters + l * 64;
+          cudaMemsetAsync(pp.counters, 0, 64 * sizeof(unsigned), s);
+          pp.row0 = tile0 * kBM;
+          pp.rows = (B - pp.row0) < nt * kBM ? (B - pp.row0) : nt * kBM;
+          int e = H == 768 ? launch_plstm_fwd<768>(pp, nt, s) : H == 512 ? launch_plstm_fwd<512>(pp, nt, s) : launch_plstm_fwd<256>(pp, nt, s);
+          SVB_TRY(e);
+        }
+        continue;
+      }
+    }
+    // ---- recurrence, per-frame form: one fused GEMM + cell kernel per frame (any H % 128 == 0, split terms)
     GemmOperands ops;
     memset(&ops, 0, sizeof(ops));
     // terms: h_hi W_hi (+ h_hi W_lo (+ h_lo W_hi)): rec_terms > 1 buys accuracy for large-magnitude weights
@@ -519,22 +660,30 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     SVB_TRY(make_operand_map(&ops.tb[1], lw.whh_lo, 4 * H, H, H, 0, 128));
     SVB_TRY(make_tmap_bf16(&ops.ta[2], w.h_lo[l], H, B, T + 1, H, BH, kBM));
     ops.tb[2] = ops.tb[0];
+    EpiLstmFwd::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    const int cslots = training ? T + 1 : 2;
+    SVB_TRY(make_tmap(&ep.t_gin, w.gin, 4, 4 * H, B, T, 4 * H, (uint64_t)B * 4 * H, 32, 128, 3));
+    SVB_TRY(make_tmap(&ep.t_c, w.c[l], 4, H, B, cslots, H, BH, 32, 128, 3));
+    SVB_TRY(make_tmap(&ep.t_hhi, w.h_hi[l], 2, H, B, T + 1, H, BH, 32, 128, 0));
+    SVB_TRY(make_tmap(&ep.t_hlo, w.h_lo[l], 2, H, B, T + 1, H, BH, 32, 128, 0));
+    if (training) SVB_TRY(make_tmap(&ep.t_gates, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, 128, 3));
+    ep.has_hlo = (l + 1 < L || rec_terms > 2) ? 1 : 0;
+    ep.has_gates = training ? 1 : 0;
+    ep.H = H;
     for (int t = 0; t < T; ++t) {
       ops.za[0] = ops.za[1] = ops.za[2] = t;
-      EpiLstmFwd::Params ep;
-      ep.gin = w.gin + (size_t)t * B * 4 * H;
-      ep.c_prev = w.c[l] + (size_t)(training ? t : (t & 1)) * BH;
-      ep.c_out = w.c[l] + (size_t)(training ? t + 1 : ((t + 1) & 1)) * BH;
-      ep.h_hi = w.h_hi[l] + (size_t)(t + 1) * BH;
-      ep.h_lo = (l + 1 < L || rec_terms > 2) ? w.h_lo[l] + (size_t)(t + 1) * BH : nullptr;
-      ep.gates = training ? w.gates[l] + (size_t)t * B * 4 * H : nullptr;
+      ep.t = t;
+      ep.c_prev_slot = training ? t : (t & 1);
+      ep.c_out_slot = training ? t + 1 : ((t + 1) & 1);
       ep.h_f32 = (l == L - 1 && t == T - 1) ? w.h_last : nullptr;
-      ep.H = H;
-      SVB_TRY((launch_step<EpiLstmFwd, 128, false>(ops, ep, s)));
+      SVB_TRY((launch_step<EpiLstmFwd, 128, 4, false>(ops, ep, s)));
     }
   }
+  prof_mark(PH_PROJ, s);
   proj_norm_kernel<<<(B + kProjRows - 1) / kProjRows, 256, (size_t)kProjRows * (H + P) * 4, s>>>(
       w.h_last, proj_w, proj_b, w.y, w.inv_norm, emb, B, H, P);
+  prof_mark(-1, s);
   SVB_CUDA("proj_norm");
   return SVB_OK;
 }
@@ -552,6 +701,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   const size_t BH = (size_t)B * H;
   const int TB = T * B;
   // ---- projection + norm backward (fp32)
+  prof_mark(PH_PROJ_BWD, s);
   norm_bwd_kernel<<<(B + 7) / 8, 256, 0, s>>>(demb, w.y, w.inv_norm, w.dy, B, P);
   sgemm_small(w.dy, w.h_last, grads[4 * L], P, H, B, 1, 0, s);          // dW_proj[P,H] = dy^T h_last
   colsum_f32_kernel<<<(P + 127) / 128, 128, 0, s>>>(w.dy, grads[4 * L + 1], B, P);
@@ -559,42 +709,49 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   SVB_CUDA("projection backward");
   for (int l = L - 1; l >= 0; --l) {
     const LayerW& lw = pw.l[l];
+    prof_mark(PH_REC_BWD, s);
     cudaMemsetAsync(w.dc, 0, BH * 4, s);
     // ---- BPTT: dh_t(rec) = dG_{t+1} W_hh  fused with the gate backward
     GemmOperands ops;
     memset(&ops, 0, sizeof(ops));
     ops.nterms = 1; ops.M = B; ops.N = H; ops.K = 4 * H;
     SVB_TRY(make_tmap_bf16(&ops.ta[0], w.gates[l], 4 * H, B, T + 1, 4 * H, (size_t)B * 4 * H, kBM));
-    SVB_TRY(make_operand_map(&ops.tb[0], lw.whh_hi, H, 4 * H, H, 1, 0));   // [K=4H rows, N=H]: MN-major
+    SVB_TRY(make_operand_map(&ops.tb[0], lw.whhT, H, 4 * H, 4 * H, 0, 32));   // [N=H rows, K=4H] K-major, 32-row box
+    EpiLstmBwd::Params ep;
+    memset(&ep, 0, sizeof(ep));
+    SVB_TRY(make_tmap(&ep.t_gates, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, 128, 3));
+    SVB_TRY(make_tmap(&ep.t_c, w.c[l], 4, H, B, T + 1, H, BH, 32, 128, 3));
+    SVB_TRY(make_tmap(&ep.t_dc, w.dc, 4, H, B, 1, H, BH, 32, 128, 3));
+    if (l == L - 1) SVB_TRY(make_tmap(&ep.t_dha, w.dh_last, 4, H, B, 1, H, BH, 32, 128, 3));
+    else SVB_TRY(make_tmap(&ep.t_dha, w.dh_above, 4, H, B, T, H, BH, 32, 128, 3));
     for (int t = T - 1; t >= 0; --t) {
       ops.za[0] = t + 1;
-      EpiLstmBwd::Params ep;
-      ep.gates = w.gates[l] + (size_t)t * B * 4 * H;
-      ep.c_t = w.c[l] + (size_t)(t + 1) * BH;
-      ep.c_prev = w.c[l] + (size_t)t * BH;
-      ep.dc = w.dc;
-      ep.dh_above = (l == L - 1) ? (t == T - 1 ? w.dh_last : nullptr) : w.dh_above + (size_t)t * BH;
-      ep.H = H;
-      ep.use_acc = 1;
-      SVB_TRY((launch_step<EpiLstmBwd, 128, true>(ops, ep, s)));
+      ep.t = t;
+      ep.has_dha = (l == L - 1) ? (t == T - 1 ? 1 : 0) : 1;
+      ep.dha_slot = (l == L - 1) ? 0 : t;
+      SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false>(ops, ep, s)));
     }
     // ---- weight gradients: dW[4H, K] = dG^T X over all T*B rows (both operands MN-major), rows unpacked on store
     const __nv_bfloat16* xin = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;
+    prof_mark(PH_WGRAD, s);
     {
       GemmOperands g;
       memset(&g, 0, sizeof(g));
       g.nterms = 1; g.M = 4 * H; g.N = H; g.K = TB;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], 4 * H, TB, 4 * H, 1, 0));
       SVB_TRY(make_operand_map(&g.tb[0], w.h_hi[l], H, TB, H, 1, 0));           // h_{t-1}: slots 0..T-1
-      EpiStoreF32::Params ep{grads[4 * l + 1], nullptr, (int64_t)H, H, H};
-      cudaError_t e = launch_tc_gemm<128, 4, true, true, EpiStoreF32>(g, ep, s);
+      EpiStoreF32<128>::Params ep;
+      SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
+      cudaError_t e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep, s);
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
       SVB_TRY(make_operand_map(&g.tb[0], xin, lw.Ip, TB, lw.Ip, 1, 0));
-      EpiStoreF32::Params ep2{grads[4 * l], nullptr, (int64_t)lw.I, lw.I, H};
-      e = launch_tc_gemm<128, 4, true, true, EpiStoreF32>(g, ep2, s);
+      EpiStoreF32<128>::Params ep2;
+      SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+      e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
       if (e != cudaSuccess) { set_error("dW_ih", e); return SVB_ERR_CUDA; }
     }
+    prof_mark(PH_BIAS, s);
     {
       const int chunks = (TB + kColsumRows - 1) / kColsumRows;
       dim3 grid((4 * H / 2 + 255) / 256, chunks);
@@ -603,16 +760,19 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       SVB_CUDA("bias grads");
     }
     // ---- gradient w.r.t. the layer input = dh_above of the layer below: dX[T*B, H] = dG W_ih
+    prof_mark(PH_DX, s);
     if (l > 0) {
       GemmOperands g;
       memset(&g, 0, sizeof(g));
       g.nterms = 1; g.M = TB; g.N = H; g.K = 4 * H;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], TB, 4 * H, 4 * H, 0, kBM));
       SVB_TRY(make_operand_map(&g.tb[0], lw.wih_hi, H, 4 * H, lw.Ip, 1, 0));
-      EpiStoreF32::Params ep{w.dh_above, nullptr, (int64_t)H, H, 0};
-      cudaError_t e = launch_tc_gemm<128, 4, false, true, EpiStoreF32>(g, ep, s);
+      EpiStoreF32<128>::Params ep;
+      SVB_TRY(make_store_params<128>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
+      cudaError_t e = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>>(g, ep, s);
       if (e != cudaSuccess) { set_error("dX", e); return SVB_ERR_CUDA; }
     }
   }
+  prof_mark(-1, s);
   return SVB_OK;
 }

@@ -3,11 +3,16 @@
 //   D[m, n] = sum_{term} sum_k A_term[m, k] * B_term[n, k]        (bf16 operands, fp32 accumulate in TMEM)
 //
 // One CTA computes one 128 x BN tile.  192 threads:
-//   warp 0      TMA producer  (cp.async.bulk.tensor into a kStages ring of 128B-swizzled tiles)
+//   warp 0      TMA producer: first the epilogue's input tiles (Epi::issue_loads), then the operand ring
+//               (cp.async.bulk.tensor into kStages 128B-swizzled stages)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, then the Epi functor
-// "Terms" accumulate several operand pairs into one accumulator; this is how the split-bf16
-// (hi/lo) input projection gets near-fp32 accuracy from bf16 tensor-core passes.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> Epi::apply, which reads its inputs from
+//               swizzled shared memory (TMA-loaded) and writes its outputs to a staging area aliased on the
+//               (by then idle) operand ring; one thread then issues TMA stores (Epi::issue_stores).
+// All bulk global traffic of the epilogue is TMA: a thread-per-row epilogue doing 16-byte global accesses touches
+// 32 cache lines per warp instruction and is L1TEX-wavefront bound (measured: 40 us of a 46 us BPTT frame).
+// "Terms" accumulate several operand pairs into one accumulator; this is how the split-bf16 (hi/lo) input
+// projection gets near-fp32 accuracy from bf16 tensor-core passes.
 // Operands are K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous; used by the
 // weight-gradient GEMMs whose reduction runs over time*batch).
 #pragma once
@@ -29,27 +34,42 @@ struct __align__(64) GemmOperands {
   int M, N, K;                   // K = reduction length per term
 };
 
-template <int BN, int kStages>
+// Byte offset of 16-byte unit `u16` of row `row` in a TMA tile whose rows are 128 bytes (SWIZZLE_128B, tile base
+// 1024-byte aligned): the unit index is XORed with (row mod 8).
+__device__ __forceinline__ uint32_t sw128(int row, int u16) { return row * 128 + ((u16 ^ (row & 7)) << 4); }
+
+template <int BN, int kStages, class Epi>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static_assert(kStageBytes % 1024 == 0, "stages must keep 1024-byte alignment");
+  static_assert(Epi::kOutBytes <= kRingBytes, "output staging is aliased on the operand ring");
+  static constexpr int kInOffset = kRingBytes;
+  static constexpr int kBarOffset = kInOffset + ((Epi::kInBytes + 1023) / 1024) * 1024;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-// Epi must provide:  struct Params;  static __device__ void apply(const Params&, int m, int n0, float (&acc)[32]);
-// and optionally a per-tile prologue.  (m, n0) are global row / first column of the 32-wide chunk.
+// Epi interface:
+//   struct Params;  static constexpr int kInBytes, kOutBytes;
+//   static __device__ void issue_loads(const Params&, uint8_t* in, uint64_t* bar, int m0, int n0);   one thread
+//   static __device__ void apply(const Params&, const uint8_t* in, uint8_t* out, int row, int m, int n0, int chunk,
+//                                float (&acc)[32], bool valid);                                   128 threads
+//   static __device__ void issue_stores(const Params&, const uint8_t* out, int m0, int n0);         one thread
 template <int BN, int kStages, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_constant__ GemmOperands ops,
-                                                               const typename Epi::Params ep) {
-  using S = GemmSmem<BN, kStages>;
+                                                               const __grid_constant__ typename Epi::Params ep) {
+  using S = GemmSmem<BN, kStages, Epi>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* in_smem = smem + S::kInOffset;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* accum_bar = empty_bar + kStages;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* in_bar = accum_bar + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(in_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int n0 = blockIdx.x * BN;
@@ -63,9 +83,10 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(in_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_holder);
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,10 +95,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      for (int t = 0; t < ops.nterms; ++t) {
-        tma_prefetch_desc(&ops.ta[t]);
-        tma_prefetch_desc(&ops.tb[t]);
-      }
+      if (Epi::kInBytes > 0) Epi::issue_loads(ep, in_smem, in_bar, m0, n0);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
           umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
-        if (it == iters - 1) umma_commit(accum_bar);  // accumulator complete
+        if (it == iters - 1) umma_commit(accum_bar);  // accumulator complete, operand ring idle
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -131,9 +149,10 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane_id();
-    typename Epi::Tile tile;
-    Epi::prologue(ep, tile, m, n0, m < ops.M);
+    const int row = q * 32 + lane_id();
+    const int m = m0 + row;
+    const bool valid = m < ops.M;
+    if (Epi::kInBytes > 0) mbar_wait(in_bar, 0);
     mbar_wait(accum_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -141,12 +160,21 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
       float acc[32];
       tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
       tmem_ld_wait();
-      if (m < ops.M && n0 + c * 32 < ops.N) Epi::apply(ep, tile, m, n0 + c * 32, acc);
+      Epi::apply(ep, in_smem, smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
+    }
+    if (Epi::kOutBytes > 0) {
+      fence_proxy_async_smem();                  // staging writes -> visible to the TMA engine
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        Epi::issue_stores(ep, smem, m0, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_d);
+  if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -155,13 +183,17 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_fn();
 
-// bf16 tensor viewed as [d2][d1][d0] (d0 contiguous); box = {64, box_rows, 1}, 128B swizzle, OOB -> 0.
+// Tensor viewed as [d2][d1][d0] (d0 contiguous), element size 2 (bf16) or 4 (fp32) bytes; box = {box0, box1, 1};
+// swizzle: 0 none, 2 = 64B, 3 = 128B (box0 * elem_bytes must equal the swizzle span); OOB -> 0 / clipped.
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1, int swizzle);
+// bf16 operand tile map: box = {64, box_rows, 1}, 128B swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows);
 
 template <int BN, int kStages, bool A_MN, bool B_MN, class Epi>
 cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t stream) {
-  using S = GemmSmem<BN, kStages>;
+  using S = GemmSmem<BN, kStages, Epi>;
   auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi>;
   static bool configured = false;
   if (!configured) {

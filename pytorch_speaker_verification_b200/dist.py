@@ -1,0 +1,83 @@
+"""Multi-GPU GE2E: one process per GPU, speakers sharded across ranks.
+
+The LSTM / projection / L2 norm are independent per utterance (pure data parallel, no exchange).  GE2E couples
+speakers only through the centroids, so the one forward exchange is an all-gather of the (N_local*M, D) d-vectors;
+every rank then evaluates the fused GE2E kernel on the global (N, M, D) batch and keeps its own slice of dL/dE
+(design "B": no backward exchange for the loss; w.grad/b.grad are identical on every rank).  Parameter gradients are
+all-reduced with SUM -- not mean -- because the reference loss is a sum over rows (utils.py:131).
+
+The reference has no distributed code at all; this module is new functionality behind the same GE2ELoss object.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def speaker_shard(n_speakers, rank, world):
+    """Contiguous speaker range [lo, hi) owned by ``rank``; requires n_speakers % world == 0."""
+    if n_speakers % world:
+        raise ValueError(f"{n_speakers} speakers do not shard evenly over {world} ranks")
+    per = n_speakers // world
+    return rank * per, (rank + 1) * per
+
+
+def _fused_loss_and_grads(E, w, b):
+    r = ops._ge2e_call(E, None, w, b, None, None, False, True, True, True)
+    return r["loss"], r["dE"], r["dw"], r["db"]
+
+
+class _GlobalGE2EFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, local_emb, w, b, group, compute):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        Nl, M, D = local_emb.shape
+        E_all = torch.empty(world * Nl, M, D, dtype=local_emb.dtype, device=local_emb.device)
+        dist.all_gather_into_tensor(E_all, local_emb.contiguous(), group=group)
+        loss, dE, dw, db = compute(E_all, w.detach(), b.detach())
+        ctx.save_for_backward(dE[rank * Nl:(rank + 1) * Nl], dw, db)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dE, dw, db = ctx.saved_tensors
+        if dE.device.type == "cuda":
+            dE, dw, db = dE.clone(), dw.clone(), db.clone()
+            ops.check(ops._lib.lib().svb_scale3(ops.ptr(dE), ops._sz(dE.numel()), ops.ptr(dw), ops._sz(1), ops.ptr(db),
+                                                ops._sz(1), ops.ptr(g.contiguous()), ops.stream_ptr()), "svb_scale3")
+        else:                       # host-logic tests (gloo, injected compute)
+            dE, dw, db = dE * g, dw * g, db * g
+        return dE, dw, db, None, None
+
+
+class GlobalGE2ELoss(torch.nn.Module):
+    """Wraps a GE2ELoss so that ``forward(local_embeddings (N_local, M, D))`` returns the loss of the GLOBAL batch
+    (the same number on every rank) and back-propagates this rank's slice of dL/dE."""
+
+    def __init__(self, criterion, group=None, compute=None):
+        super().__init__()
+        self.criterion = criterion
+        self.group = group
+        self.compute = compute or _fused_loss_and_grads
+
+    def forward(self, local_embeddings):
+        return _GlobalGE2EFn.apply(local_embeddings, self.criterion.w, self.criterion.b, self.group, self.compute)
+
+
+def allreduce_gradients(params, group=None):
+    """SUM all-reduce of the parameter gradients (one NCCL call when the grads are views of one flat buffer, as
+    EmbedderFn.backward produces them)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    base = grads[0]._base if grads[0]._base is not None else None
+    if base is not None and all(g._base is base for g in grads) and sum(g.numel() for g in grads) == base.numel():
+        dist.all_reduce(base, op=dist.ReduceOp.SUM, group=group)
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

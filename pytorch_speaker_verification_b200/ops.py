@@ -31,6 +31,11 @@ def _stage(t, dtype=None):
     return t.contiguous()
 
 
+def set_persistent(on):
+    """Select the recurrent forward kernel: True (default) persistent cooperative kernel, False per-frame launches."""
+    check(_lib.lib().svb_set_persistent(int(bool(on))), "svb_set_persistent")
+
+
 def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
@@ -95,7 +100,12 @@ class EmbedderFn(torch.autograd.Function):
         B, T, I, H, L, P = ctx.shape
         with torch.cuda.device(ctx.ws.device):
             dg = _stage(demb, torch.float32)
-            grads = [torch.empty_like(p) for p in ctx.dev_params]
+            # one flat buffer, parameters as views: a single all-reduce covers every gradient (dist.py)
+            flat = torch.empty(sum(p.numel() for p in ctx.dev_params), dtype=torch.float32, device=dg.device)
+            grads, off = [], 0
+            for p in ctx.dev_params:
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
             check(_lib.lib().svb_embedder_backward(ptr(dg), ptr(ctx.packed), ptr(ctx.dev_params[4 * L]),
                                                    _ptr_array(grads), ptr(ctx.ws), B, T, I, H, L, P, stream_ptr()),
                   "svb_embedder_backward")

@@ -1,0 +1,19 @@
+"""One warm-up + one measured C2 train step (fwd + GE2E + bwd) for ncu captures."""
+import sys
+import torch
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import _inputs as I
+import pytorch_speaker_verification_b200 as svb
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+torch.manual_seed(0)
+net = svb.SpeechEmbedder().cuda()
+crit = svb.GE2ELoss("cuda")
+x = torch.tensor(I.logmel(640, 160, seed=1234)).cuda()
+for i in range(steps):
+    for p in net.parameters():
+        p.grad = None
+    loss = crit(net(x).reshape(64, 10, 256))
+    loss.backward()
+    torch.cuda.synchronize()
+print("loss", loss.item())

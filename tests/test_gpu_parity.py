@@ -240,6 +240,30 @@ def test_embedder_forward_matches_reference(svb, net):
     print("embedding err C1:", emb_err(e, g["emb"]), "T24:", emb_err(e24, g["emb_T24"]))
 
 
+def test_persistent_and_per_frame_kernels_agree(svb, net):
+    """The persistent recurrent kernel (W_hh resident in smem, h staged through TMEM, flag barriers per batch
+    tile) and the per-frame kernels compute the same embeddings and the same BPTT stash."""
+    from pytorch_speaker_verification_b200 import ops
+    g = load("embedder_c1.npz")
+    x = torch.tensor(I.logmel(20, 180, seed=1234)).cuda()
+    xb = torch.tensor(I.logmel(300, 50, seed=77)).cuda()          # 3 batch tiles, ragged last tile
+    try:
+        out = {}
+        for mode in (True, False):
+            ops.set_persistent(mode)
+            with torch.no_grad():
+                out[mode] = (net(x), net(xb))
+            net.zero_grad()
+            e = net(xb[:140])
+            e.square().sum().mul(0.5).add(e.sum()).backward()
+            out[mode] += (net.LSTM_stack.weight_hh_l0.grad.clone(), net.LSTM_stack.weight_ih_l2.grad.clone())
+    finally:
+        ops.set_persistent(False)
+    assert emb_err(out[True][0].cpu().numpy(), g["emb"]) < 1e-3
+    for a, b in zip(out[True], out[False]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (a - b).abs().max()
+
+
 def test_embedder_saturated_weights(svb):
     g = load("embedder_saturated.npz")
     sat = I.saturating_weights({k: v.numpy() for k, v in oemb.init_state_dict(seed=0).items()})
