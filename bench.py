@@ -248,7 +248,7 @@ def main():
     ms_value = timed(value_step, args.steps, args.warmup)
     ms_e2e = timed(full_step, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    phases = phase_profile(value_step) if rank == 0 else None
+    phases = phase_profile(value_step)          # every rank: the step contains collectives
     barrier()
     loss_val = float(loss_host)
 

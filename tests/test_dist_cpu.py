@@ -1,0 +1,86 @@
+"""CPU, world_size 2, gloo: host-side logic of the multi-GPU path (speaker sharding, d-vector all-gather, slice of
+dL/dE kept per rank, SUM all-reduce of parameter gradients).  The fused CUDA kernel is replaced by the oracle's
+closed form through GlobalGE2ELoss's injection point (tests may use the oracle; the product default is the kernel)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _inputs as I
+from oracle import ge2e as oge2e
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_compute(E, w, b):
+    r = oge2e.ge2e_fwd_bwd(E.numpy(), float(w), float(b))
+    f = lambda v: torch.tensor(np.asarray(v, dtype=np.float32))
+    return f(r["loss"]), f(r["dE"]), f(r["dw"]), f(r["db"])
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pytorch_speaker_verification_b200.dist import GlobalGE2ELoss, allreduce_gradients, speaker_shard
+
+    N, M, D = 8, 3, 16
+    E = I.ge2e_embeddings(N, M, D, "raw")
+    lo, hi = speaker_shard(N, rank, world)
+    # a stand-in "embedder": emb = x @ W, shared W, so that parameter gradients need the all-reduce
+    torch.manual_seed(0)
+    W = torch.nn.Parameter(torch.eye(D) + 0.01 * torch.randn(D, D))
+
+    class Crit(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(3.0))
+            self.b = torch.nn.Parameter(torch.tensor(-1.0))
+
+    crit = Crit()
+    gl = GlobalGE2ELoss(crit, compute=_oracle_compute)
+    x_local = torch.tensor(E[lo:hi])
+    loss = gl(x_local @ W)
+    (loss * 0.5).backward()
+    allreduce_gradients([W])
+    out[rank] = (loss.item(), W.grad.clone(), crit.w.grad.item(), crit.b.grad.item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_global_ge2e_two_ranks_matches_single_process():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    # single-process reference: whole batch through the oracle-backed autograd path
+    N, M, D = 8, 3, 16
+    E = torch.tensor(I.ge2e_embeddings(N, M, D, "raw"))
+    torch.manual_seed(0)
+    W = torch.nn.Parameter(torch.eye(D) + 0.01 * torch.randn(D, D))
+    emb = E @ W
+    r = oge2e.ge2e_fwd_bwd(emb.detach().numpy(), 3.0, -1.0)
+    emb.backward(torch.tensor(0.5 * r["dE"]))
+    for rank in range(world):
+        loss, gW, gw, gb = out[rank]
+        assert abs(loss - float(r["loss"])) < 1e-4 * abs(float(r["loss"]))      # same global loss on every rank
+        assert torch.allclose(gW, W.grad, rtol=1e-4, atol=1e-6)                  # SUM over ranks == global gradient
+        assert abs(gw - 0.5 * float(r["dw"])) < 1e-4 * abs(float(r["dw"]))       # identical on every rank, not summed
+        assert abs(gb - 0.5 * float(r["db"])) < 1e-3 * abs(float(r["db"])) + 1e-7
+
+
+def test_speaker_shard():
+    from pytorch_speaker_verification_b200.dist import speaker_shard
+    assert [speaker_shard(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
+    with pytest.raises(ValueError):
+        speaker_shard(10, 0, 4)

@@ -1,0 +1,66 @@
+"""GPU, 2 ranks over NCCL: the sharded global GE2E step equals the single-GPU step on the concatenated batch
+(BASELINE configs[2] semantics at world_size 2).  Skipped on a 1-GPU box."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _inputs as I
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import pytorch_speaker_verification_b200 as svb
+    from pytorch_speaker_verification_b200.dist import GlobalGE2ELoss, allreduce_gradients, speaker_shard
+    torch.manual_seed(0)
+    net = svb.SpeechEmbedder().cuda()
+    crit = svb.GE2ELoss("cuda")
+    N, M, T = 8, 4, 30
+    x = torch.tensor(I.logmel(N * M, T, seed=42)).reshape(N, M, T, 40)
+    lo, hi = speaker_shard(N, rank, world)
+    emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
+    loss = GlobalGE2ELoss(crit)(emb.reshape(hi - lo, M, -1))
+    loss.backward()
+    allreduce_gradients(list(net.parameters()))
+    out[rank] = (loss.item(), net.LSTM_stack.weight_hh_l1.grad.cpu(), net.projection.weight.grad.cpu(),
+                 crit.w.grad.item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_step_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    import pytorch_speaker_verification_b200 as svb
+    torch.manual_seed(0)
+    net = svb.SpeechEmbedder().cuda()
+    crit = svb.GE2ELoss("cuda")
+    N, M, T = 8, 4, 30
+    x = torch.tensor(I.logmel(N * M, T, seed=42)).cuda()
+    loss = crit(net(x).reshape(N, M, -1))
+    loss.backward()
+    for rank in range(2):
+        l, g1, gp, gw = out[rank]
+        assert abs(l - loss.item()) < 1e-5 * abs(loss.item())
+        assert torch.allclose(g1, net.LSTM_stack.weight_hh_l1.grad.cpu(), rtol=2e-3, atol=1e-6)
+        assert torch.allclose(gp, net.projection.weight.grad.cpu(), rtol=2e-3, atol=1e-6)
+        assert abs(gw - crit.w.grad.item()) < 1e-4 * abs(crit.w.grad.item())
