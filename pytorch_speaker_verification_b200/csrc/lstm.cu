@@ -507,6 +507,7 @@ struct Profiler {
 };
 static Profiler g_prof;
 static int g_persistent = 0;
+static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
 static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
   if (!g_prof.on || g_prof.n >= 256) return;
   if (g_prof.n >= g_prof.created) { cudaEventCreate(&g_prof.ev[g_prof.created]); g_prof.created++; }
@@ -537,6 +538,7 @@ using namespace svb;
 
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
+extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
 extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
 // Sums the elapsed ms per phase since the last enable/read; the caller must have synchronised the stream.
 extern "C" int svb_profile_read(float* ms_per_phase, int nphases) {
@@ -673,6 +675,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     ep.H = H;
     for (int t = 0; t < T; ++t) {
       ops.za[0] = ops.za[1] = ops.za[2] = t;
+      ops.trace = (g_trace && l == 1 && t == T / 2) ? g_trace : nullptr;
       ep.t = t;
       ep.c_prev_slot = training ? t : (t & 1);
       ep.c_out_slot = training ? t + 1 : ((t + 1) & 1);
@@ -726,6 +729,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     else SVB_TRY(make_tmap(&ep.t_dha, w.dh_above, 4, H, B, T, H, BH, 32, 128, 3));
     for (int t = T - 1; t >= 0; --t) {
       ops.za[0] = t + 1;
+      ops.trace = (g_trace && l == 1 && t == T / 2) ? g_trace + 4096 : nullptr;
       ep.t = t;
       ep.has_dha = (l == L - 1) ? (t == T - 1 ? 1 : 0) : 1;
       ep.dha_slot = (l == L - 1) ? 0 : t;

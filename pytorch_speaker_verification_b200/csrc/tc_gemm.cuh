@@ -32,6 +32,7 @@ struct __align__(64) GemmOperands {
   int zb[kMaxTerms];
   int nterms;
   int M, N, K;                   // K = reduction length per term
+  unsigned long long* trace;     // debug: 16 globaltimer stamps per CTA, or null
 };
 
 // Byte offset of 16-byte unit `u16` of row `row` in a TMA tile whose rows are 128 bytes (SWIZZLE_128B, tile base
@@ -51,6 +52,14 @@ struct GemmSmem {
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmOperands& ops, int slot) {
+  if (ops.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    ops.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+  }
+}
 
 // Epi interface:
 //   struct Params;  static constexpr int kInBytes, kOutBytes;
@@ -78,6 +87,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   const int iters = nkb * ops.nterms;
 
   if (threadIdx.x == 0) {
+    trace_stamp(ops, 0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -95,6 +105,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      trace_stamp(ops, 1);
       if (Epi::kInBytes > 0) Epi::issue_loads(ep, in_smem, in_bar, m0, n0);
       int stage = 0;
       uint32_t phase = 0;
@@ -119,6 +130,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      trace_stamp(ops, 2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -129,6 +141,8 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
+        if (it == 0) trace_stamp(ops, 3);
+        if (it == iters - 1) trace_stamp(ops, 4);
         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
         const uint32_t sb = sa + S::kABytes;
 #pragma unroll
@@ -153,8 +167,10 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
     const int m = m0 + row;
     const bool valid = m < ops.M;
     if (Epi::kInBytes > 0) mbar_wait(in_bar, 0);
+    if (threadIdx.x == 64) trace_stamp(ops, 5);
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(ops, 6);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float acc[32];
@@ -162,19 +178,23 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
       tmem_ld_wait();
       Epi::apply(ep, in_smem, smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
     }
+    if (threadIdx.x == 64) trace_stamp(ops, 7);
     if (Epi::kOutBytes > 0) {
       fence_proxy_async_smem();                  // staging writes -> visible to the TMA engine
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
+        trace_stamp(ops, 8);
         Epi::issue_stores(ep, smem, m0, n0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        trace_stamp(ops, 9);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
+  if (threadIdx.x == 0) trace_stamp(ops, 10);
 }
 
 // ----------------------------------------------------------------------------- host side
