@@ -526,9 +526,9 @@ static int check_dims(const Dims& d) {
   return SVB_OK;
 }
 
-template <class Epi, int BN, int kStages, bool B_MN>
+template <class Epi, int BN, int kStages, bool B_MN, int kEpiWarps>
 static int launch_step(GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t s) {
-  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi>(ops, ep, s);
+  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi, kEpiWarps>(ops, ep, s);
   if (e != cudaSuccess) { set_error("lstm step launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }
@@ -620,7 +620,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       }
       EpiStoreF32<128>::Params ep;
       SVB_TRY(make_store_params<128>(&ep, w.gin, lw.bias, T * B, 4 * H, (int64_t)4 * H, 0));
-      cudaError_t e = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>>(ops, ep, s);
+      cudaError_t e = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>, 8>(ops, ep, s);
       if (e != cudaSuccess) { set_error("input projection", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_REC_FWD, s);
@@ -680,7 +680,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       ep.c_prev_slot = training ? t : (t & 1);
       ep.c_out_slot = training ? t + 1 : ((t + 1) & 1);
       ep.h_f32 = (l == L - 1 && t == T - 1) ? w.h_last : nullptr;
-      SVB_TRY((launch_step<EpiLstmFwd, 128, 4, false>(ops, ep, s)));
+      SVB_TRY((launch_step<EpiLstmFwd, 128, 4, false, 8>(ops, ep, s)));
     }
   }
   prof_mark(PH_PROJ, s);
@@ -733,7 +733,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       ep.t = t;
       ep.has_dha = (l == L - 1) ? (t == T - 1 ? 1 : 0) : 1;
       ep.dha_slot = (l == L - 1) ? 0 : t;
-      SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false>(ops, ep, s)));
+      SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false, 4>(ops, ep, s)));
     }
     // ---- weight gradients: dW[4H, K] = dG^T X over all T*B rows (both operands MN-major), rows unpacked on store
     const __nv_bfloat16* xin = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;

@@ -22,7 +22,6 @@ namespace svb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 192;
 constexpr int kMaxTerms = 3;
 
 struct __align__(64) GemmOperands {
@@ -67,8 +66,9 @@ __device__ __forceinline__ void trace_stamp(const GemmOperands& ops, int slot) {
 //   static __device__ void apply(const Params&, const uint8_t* in, uint8_t* out, int row, int m, int n0, int chunk,
 //                                float (&acc)[32], bool valid);                                   128 threads
 //   static __device__ void issue_stores(const Params&, const uint8_t* out, int m0, int n0);         one thread
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_constant__ GemmOperands ops,
+// kEpiWarps = 4 or 8 epilogue warps (8: two warps per TMEM lane quarter, each taking half of the column chunks).
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __grid_constant__ GemmOperands ops,
                                                                const __grid_constant__ typename Epi::Params ep) {
   using S = GemmSmem<BN, kStages, Epi>;
   extern __shared__ uint8_t smem_raw[];
@@ -86,6 +86,13 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   const int nkb = (ops.K + kBK - 1) / kBK;
   const int iters = nkb * ops.nterms;
 
+  // Programmatic dependent launch: let the next kernel of the stream begin its launch/prologue now; our own reads
+  // of the previous kernel's results are ordered by griddepcontrol.wait below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 32) {
+    tma_prefetch_desc(&ops.ta[0]);
+    tma_prefetch_desc(&ops.tb[0]);
+  }
   if (threadIdx.x == 0) {
     trace_stamp(ops, 0);
     for (int s = 0; s < kStages; ++s) {
@@ -97,6 +104,7 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_holder);
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // previous kernel complete and its writes visible
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,10 +114,13 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       trace_stamp(ops, 1);
-      if (Epi::kInBytes > 0) Epi::issue_loads(ep, in_smem, in_bar, m0, n0);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
+        // the epilogue's input tiles are requested once the ring is primed, so that the first MMA is not queued
+        // behind them in the TMA unit
+        if (Epi::kInBytes > 0 && it == (kStages < iters ? kStages : iters - 1))
+          Epi::issue_loads(ep, in_smem, in_bar, m0, n0);
         const int term = it / nkb;
         const int k0 = (it - term * nkb) * kBK;
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -163,6 +174,9 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;            // 0 (or 1 with 8 epilogue warps)
+    constexpr int kChunks = BN / 32;
+    constexpr int kPerWarp = (kEpiWarps == 8 && kChunks >= 2) ? kChunks / 2 : kChunks;
     const int row = q * 32 + lane_id();
     const int m = m0 + row;
     const bool valid = m < ops.M;
@@ -171,17 +185,20 @@ __global__ void __launch_bounds__(kGemmThreads) tc_gemm_kernel(const __grid_cons
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(ops, 6);
+    if (kEpiWarps == 4 || kChunks >= 2 || half == 0) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float acc[32];
-      tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
-      tmem_ld_wait();
-      Epi::apply(ep, in_smem, smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
+      for (int cc = 0; cc < kPerWarp; ++cc) {
+        const int c = (kEpiWarps == 8 && kChunks >= 2) ? half * kPerWarp + cc : cc;
+        float acc[32];
+        tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
+        tmem_ld_wait();
+        Epi::apply(ep, in_smem, smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
+      }
     }
     if (threadIdx.x == 64) trace_stamp(ops, 7);
     if (Epi::kOutBytes > 0) {
       fence_proxy_async_smem();                  // staging writes -> visible to the TMA engine
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       if (threadIdx.x == 64) {
         trace_stamp(ops, 8);
         Epi::issue_stores(ep, smem, m0, n0);
@@ -211,19 +228,28 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, u
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows);
 
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi>
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4>
 cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages, Epi>;
-  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi>;
+  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((ops.N + BN - 1) / BN, (ops.M + kBM - 1) / kBM);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(ops, ep);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((ops.N + BN - 1) / BN, (ops.M + kBM - 1) / kBM);
+  cfg.blockDim = dim3(64 + 32 * kEpiWarps);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ops, ep);
 }
 
 }  // namespace svb
