@@ -310,44 +310,62 @@ struct EpiLstmBwd {
     v[0] = bf16_lo_of(w.x); v[1] = bf16_hi_of(w.x); v[2] = bf16_lo_of(w.y); v[3] = bf16_hi_of(w.y);
     v[4] = bf16_lo_of(w.z); v[5] = bf16_hi_of(w.z); v[6] = bf16_lo_of(w.w); v[7] = bf16_hi_of(w.w);
   }
+  // one group of 8 hidden units (q = 0..3 within the CTA's 32 units); dh8 = recurrent part of dL/dh for them
+  static __device__ __forceinline__ void apply_q(const Params& p, const uint8_t* in, uint8_t* out, int row, int q,
+                                                 const float (&dh8)[8]) {
+    const uint8_t* gb = in + kG + (q >> 1) * 16384;
+    const int ub = (q & 1) * 4;
+    float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dcs[8], dha[8];
+    unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 0)), gi);
+    unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 1)), gf);
+    unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 2)), gg);
+    unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 3)), go);
+    ld8(in + kCt, row, 2 * q, ct);
+    ld8(in + kCp, row, 2 * q, cp);
+    ld8(in + kDc, row, 2 * q, dcs);
+    if (p.has_dha) ld8(in + kDha, row, 2 * q, dha);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dha[j] = 0.f;
+    }
+    float di[8], df[8], dg[8], dO[8], dcn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dh = dh8[j] + dha[j];
+      const float tc = tanhf_fast(ct[j]);
+      const float dc = dh * go[j] * (1.f - tc * tc) + dcs[j];
+      dO[j] = dh * tc * go[j] * (1.f - go[j]);
+      di[j] = dc * gg[j] * gi[j] * (1.f - gi[j]);
+      df[j] = dc * cp[j] * gf[j] * (1.f - gf[j]);
+      dg[j] = dc * gi[j] * (1.f - gg[j] * gg[j]);
+      dcn[j] = dc * gf[j];
+    }
+    uint8_t* og = out + kOg + (q >> 1) * 16384;
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8(di);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8(df);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8(dg);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8(dO);
+    *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+    *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q + 1)) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+  }
   static __device__ __forceinline__ void apply(const Params& p, const uint8_t* in, uint8_t* out, int row, int, int,
                                                int, float (&acc)[32], bool) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                       // 8 units each
-      const uint8_t* gb = in + kG + (q >> 1) * 16384;
-      const int ub = (q & 1) * 4;
-      float gi[8], gf[8], gg[8], go[8], ct[8], cp[8], dcs[8], dha[8];
-      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 0)), gi);
-      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 1)), gf);
-      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 2)), gg);
-      unpack8(*reinterpret_cast<const uint4*>(gb + sw128(row, ub + 3)), go);
-      ld8(in + kCt, row, 2 * q, ct);
-      ld8(in + kCp, row, 2 * q, cp);
-      ld8(in + kDc, row, 2 * q, dcs);
-      if (p.has_dha) ld8(in + kDha, row, 2 * q, dha);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dha[j] = 0.f;
-      }
-      float di[8], df[8], dg[8], dO[8], dcn[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dh = acc[8 * q + j] + dha[j];
-        const float tc = tanhf_fast(ct[j]);
-        const float dc = dh * go[j] * (1.f - tc * tc) + dcs[j];
-        dO[j] = dh * tc * go[j] * (1.f - go[j]);
-        di[j] = dc * gg[j] * gi[j] * (1.f - gi[j]);
-        df[j] = dc * cp[j] * gf[j] * (1.f - gf[j]);
-        dg[j] = dc * gi[j] * (1.f - gg[j] * gg[j]);
-        dcn[j] = dc * gf[j];
-      }
-      uint8_t* og = out + kOg + (q >> 1) * 16384;
-      *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8(di);
-      *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8(df);
-      *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8(dg);
-      *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8(dO);
-      *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-      *reinterpret_cast<float4*>(out + kOdc + sw128(row, 2 * q + 1)) = make_float4(dcn[4], dcn[5], dcn[6], dcn[7]);
+    for (int q = 0; q < 4; ++q) {
+      const float dh8[8] = {acc[8 * q], acc[8 * q + 1], acc[8 * q + 2], acc[8 * q + 3],
+                            acc[8 * q + 4], acc[8 * q + 5], acc[8 * q + 6], acc[8 * q + 7]};
+      apply_q(p, in, out, row, q, dh8);
+    }
+  }
+  // split-K path: `src` is the reduced [128 x 32] fp32 chunk in the swizzled tile layout; part = 0/1 of 2
+  static __device__ __forceinline__ void apply_from_smem(const Params& p, const uint8_t* in, uint8_t* out,
+                                                         const uint8_t* src, int row, int part, int nparts) {
+    const int per = 4 / nparts;
+#pragma unroll 1
+    for (int q = part * per; q < (part + 1) * per; ++q) {
+      float dh8[8];
+      ld8(src, row, 2 * q, dh8);
+      apply_q(p, in, out, row, q, dh8);
     }
   }
   static __device__ __forceinline__ void issue_stores(const Params& p, const uint8_t* out, int m0, int n0) {
@@ -507,6 +525,7 @@ struct Profiler {
 };
 static Profiler g_prof;
 static int g_persistent = 0;
+static int g_bwd_splitk = 1;   // BPTT frame: 4-CTA cluster split-K with DSMEM partial exchange
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
 static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
   if (!g_prof.on || g_prof.n >= 256) return;
@@ -526,9 +545,9 @@ static int check_dims(const Dims& d) {
   return SVB_OK;
 }
 
-template <class Epi, int BN, int kStages, bool B_MN, int kEpiWarps>
+template <class Epi, int BN, int kStages, bool B_MN, int kEpiWarps, int KSPLIT = 1>
 static int launch_step(GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t s) {
-  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi, kEpiWarps>(ops, ep, s);
+  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi, kEpiWarps, KSPLIT>(ops, ep, s);
   if (e != cudaSuccess) { set_error("lstm step launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }
@@ -538,6 +557,7 @@ using namespace svb;
 
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
+extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
 extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
 extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
 // Sums the elapsed ms per phase since the last enable/read; the caller must have synchronised the stream.
@@ -616,11 +636,12 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       const void* Bs[3] = {lw.wih_hi, lw.wih_hi, lw.wih_lo};
       for (int t = 0; t < 3; ++t) {
         SVB_TRY(make_operand_map(&ops.ta[t], As[t], T * B, lw.Ip, lw.Ip, 0, kBM));
-        SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 128));
+        SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 256));
       }
-      EpiStoreF32<128>::Params ep;
-      SVB_TRY(make_store_params<128>(&ep, w.gin, lw.bias, T * B, 4 * H, (int64_t)4 * H, 0));
-      cudaError_t e = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>, 8>(ops, ep, s);
+      // 128 x 256 tiles: a 128 x 128 tile needs 128 B/clk of operands, twice what one SM can pull from L2
+      EpiStoreF32<256>::Params ep;
+      SVB_TRY(make_store_params<256>(&ep, w.gin, lw.bias, T * B, 4 * H, (int64_t)4 * H, 0));
+      cudaError_t e = launch_tc_gemm<256, 4, false, false, EpiStoreF32<256>, 8>(ops, ep, s);
       if (e != cudaSuccess) { set_error("input projection", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_REC_FWD, s);
@@ -719,7 +740,8 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     memset(&ops, 0, sizeof(ops));
     ops.nterms = 1; ops.M = B; ops.N = H; ops.K = 4 * H;
     SVB_TRY(make_tmap_bf16(&ops.ta[0], w.gates[l], 4 * H, B, T + 1, 4 * H, (size_t)B * 4 * H, kBM));
-    SVB_TRY(make_operand_map(&ops.tb[0], lw.whhT, H, 4 * H, 4 * H, 0, 32));   // [N=H rows, K=4H] K-major, 32-row box
+    // [N=H rows, K=4H] K-major; split-K: 128-unit tiles, 4 CTAs per tile; otherwise 32-unit tiles
+    SVB_TRY(make_operand_map(&ops.tb[0], lw.whhT, H, 4 * H, 4 * H, 0, g_bwd_splitk ? 128 : 32));
     EpiLstmBwd::Params ep;
     memset(&ep, 0, sizeof(ep));
     SVB_TRY(make_tmap(&ep.t_gates, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, 128, 3));
@@ -733,7 +755,8 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       ep.t = t;
       ep.has_dha = (l == L - 1) ? (t == T - 1 ? 1 : 0) : 1;
       ep.dha_slot = (l == L - 1) ? 0 : t;
-      SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false, 4>(ops, ep, s)));
+      if (g_bwd_splitk) SVB_TRY((launch_step<EpiLstmBwd, 128, 4, false, 8, 4>(ops, ep, s)));
+      else SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false, 4>(ops, ep, s)));
     }
     // ---- weight gradients: dW[4H, K] = dG^T X over all T*B rows (both operands MN-major), rows unpacked on store
     const __nv_bfloat16* xin = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;
@@ -744,15 +767,28 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       g.nterms = 1; g.M = 4 * H; g.N = H; g.K = TB;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], 4 * H, TB, 4 * H, 1, 0));
       SVB_TRY(make_operand_map(&g.tb[0], w.h_hi[l], H, TB, H, 1, 0));           // h_{t-1}: slots 0..T-1
-      EpiStoreF32<128>::Params ep;
-      SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
-      cudaError_t e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep, s);
+      cudaError_t e;
+      if (false && H % 256 == 0) {
+        EpiStoreF32<256>::Params ep;
+        SVB_TRY(make_store_params<256>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
+        e = launch_tc_gemm<256, 4, true, true, EpiStoreF32<256>>(g, ep, s);
+      } else {
+        EpiStoreF32<128>::Params ep;
+        SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
+        e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep, s);
+      }
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
       SVB_TRY(make_operand_map(&g.tb[0], xin, lw.Ip, TB, lw.Ip, 1, 0));
-      EpiStoreF32<128>::Params ep2;
-      SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
-      e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
+      if (false && lw.I % 256 == 0) {
+        EpiStoreF32<256>::Params ep2;
+        SVB_TRY(make_store_params<256>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        e = launch_tc_gemm<256, 4, true, true, EpiStoreF32<256>>(g, ep2, s);
+      } else {
+        EpiStoreF32<128>::Params ep2;
+        SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
+      }
       if (e != cudaSuccess) { set_error("dW_ih", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_BIAS, s);
@@ -771,9 +807,16 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       g.nterms = 1; g.M = TB; g.N = H; g.K = 4 * H;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], TB, 4 * H, 4 * H, 0, kBM));
       SVB_TRY(make_operand_map(&g.tb[0], lw.wih_hi, H, 4 * H, lw.Ip, 1, 0));
-      EpiStoreF32<128>::Params ep;
-      SVB_TRY(make_store_params<128>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
-      cudaError_t e = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>>(g, ep, s);
+      cudaError_t e;
+      if (H % 256 == 0) {
+        EpiStoreF32<256>::Params ep;
+        SVB_TRY(make_store_params<256>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
+        e = launch_tc_gemm<256, 4, false, true, EpiStoreF32<256>, 8>(g, ep, s);
+      } else {
+        EpiStoreF32<128>::Params ep;
+        SVB_TRY(make_store_params<128>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
+        e = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>, 8>(g, ep, s);
+      }
       if (e != cudaSuccess) { set_error("dX", e); return SVB_ERR_CUDA; }
     }
   }

@@ -38,14 +38,16 @@ struct __align__(64) GemmOperands {
 // 1024-byte aligned): the unit index is XORed with (row mod 8).
 __device__ __forceinline__ uint32_t sw128(int row, int u16) { return row * 128 + ((u16 ^ (row & 7)) << 4); }
 
-template <int BN, int kStages, class Epi>
+template <int BN, int kStages, class Epi, int KSPLIT = 1>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static_assert(kStageBytes % 1024 == 0, "stages must keep 1024-byte alignment");
-  static_assert(Epi::kOutBytes <= kRingBytes, "output staging is aliased on the operand ring");
+  // split-K: the KSPLIT partial 32-column chunks (16 KB each) + the output staging live in the idle ring
+  static constexpr int kRecvBytes = KSPLIT > 1 ? KSPLIT * 16384 : 0;
+  static_assert(kRecvBytes + Epi::kOutBytes <= kRingBytes, "output staging is aliased on the operand ring");
   static constexpr int kInOffset = kRingBytes;
   static constexpr int kBarOffset = kInOffset + ((Epi::kInBytes + 1023) / 1024) * 1024;
   static constexpr int kTotal = kBarOffset + 256 + 1024;   // barriers + alignment slack
@@ -67,10 +69,15 @@ __device__ __forceinline__ void trace_stamp(const GemmOperands& ops, int slot) {
 //                                float (&acc)[32], bool valid);                                   128 threads
 //   static __device__ void issue_stores(const Params&, const uint8_t* out, int m0, int n0);         one thread
 // kEpiWarps = 4 or 8 epilogue warps (8: two warps per TMEM lane quarter, each taking half of the column chunks).
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4>
+// KSPLIT > 1 (requires BN == 32*KSPLIT, 4 epilogue warps, a (KSPLIT,1,1) cluster launch): the KSPLIT CTAs of a
+// cluster each reduce a 1/KSPLIT slice of K for the same 128 x BN tile, exchange their partial 32-column chunks
+// through distributed shared memory, and CTA r finishes columns [32r, 32r+32) with Epi.  Each SM then pulls only
+// 1/KSPLIT of both operands from L2 -- the per-SM L2->SM port (~64 B/clk) is what bounds the BPTT frame.
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __grid_constant__ GemmOperands ops,
                                                                const __grid_constant__ typename Epi::Params ep) {
-  using S = GemmSmem<BN, kStages, Epi>;
+  using S = GemmSmem<BN, kStages, Epi, KSPLIT>;
+  static_assert(KSPLIT == 1 || (BN == 32 * KSPLIT), "split-K layout");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* in_smem = smem + S::kInOffset;
@@ -81,10 +88,14 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(in_bar + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int n0 = blockIdx.x * BN;
+  const int kq = KSPLIT > 1 ? (int)cluster_ctarank() : 0;       // K slice (and finished column chunk) of this CTA
+  const int n0 = (blockIdx.x / KSPLIT) * BN;
   const int m0 = blockIdx.y * kBM;
-  const int nkb = (ops.K + kBK - 1) / kBK;
+  const int nkb = ((ops.K + kBK - 1) / kBK) / KSPLIT;            // host guarantees divisibility
+  const int kbase = kq * nkb * kBK;
   const int iters = nkb * ops.nterms;
+  const int n_epi = KSPLIT > 1 ? n0 + 32 * kq : n0;              // first column this CTA's epilogue owns
+  uint8_t* out_smem = smem + S::kRecvBytes;
 
   // Programmatic dependent launch: let the next kernel of the stream begin its launch/prologue now; our own reads
   // of the previous kernel's results are ordered by griddepcontrol.wait below.
@@ -120,9 +131,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
         // the epilogue's input tiles are requested once the ring is primed, so that the first MMA is not queued
         // behind them in the TMA unit
         if (Epi::kInBytes > 0 && it == (kStages < iters ? kStages : iters - 1))
-          Epi::issue_loads(ep, in_smem, in_bar, m0, n0);
+          Epi::issue_loads(ep, in_smem, in_bar, m0, n_epi);
         const int term = it / nkb;
-        const int k0 = (it - term * nkb) * kBK;
+        const int k0 = kbase + (it - term * nkb) * kBK;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;            // 0 (or 1 with 8 epilogue warps)
     constexpr int kChunks = BN / 32;
@@ -185,28 +196,89 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(ops, 6);
-    if (kEpiWarps == 4 || kChunks >= 2 || half == 0) {
+    if constexpr (KSPLIT == 1) {
+      if (kEpiWarps == 4 || kChunks >= 2 || half == 0) {
 #pragma unroll 1
-      for (int cc = 0; cc < kPerWarp; ++cc) {
-        const int c = (kEpiWarps == 8 && kChunks >= 2) ? half * kPerWarp + cc : cc;
+        for (int cc = 0; cc < kPerWarp; ++cc) {
+          const int c = (kEpiWarps == 8 && kChunks >= 2) ? half * kPerWarp + cc : cc;
+          float acc[32];
+          tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
+          tmem_ld_wait();
+          Epi::apply(ep, in_smem, out_smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
+        }
+      }
+      if (threadIdx.x == 64) trace_stamp(ops, 7);
+      if (Epi::kOutBytes > 0) {
+        fence_proxy_async_smem();                  // staging writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 64) {
+          trace_stamp(ops, 8);
+          Epi::issue_stores(ep, out_smem, m0, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          trace_stamp(ops, 9);
+        }
+      }
+    }
+  }
+  if constexpr (KSPLIT > 1) {
+    // ---- split-K exchange (pull): every CTA parks its four partial chunks in its own (idle) ring in the swizzled
+    //      tile layout; after one cluster barrier the owner of chunk kq sums the three remote copies with
+    //      lane-contiguous (coalesced) distributed-shared-memory loads, in place, then reads its rows back.
+    const int q = warp & 3;
+    const int row = q * 32 + lane_id();
+    if (warp >= 2 && warp < 6) {
+#pragma unroll 1
+      for (int c = 0; c < KSPLIT; ++c) {
         float acc[32];
         tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
         tmem_ld_wait();
-        Epi::apply(ep, in_smem, smem, row, m, n0, c, acc, valid && (n0 + c * 32 < ops.N));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(smem + c * 16384 + sw128(row, j)) =
+              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
       }
     }
-    if (threadIdx.x == 64) trace_stamp(ops, 7);
-    if (Epi::kOutBytes > 0) {
-      fence_proxy_async_smem();                  // staging writes -> visible to the TMA engine
+    cluster_sync_all();                                              // all partials parked
+    if (warp >= 2) {
+      if (threadIdx.x == 64) trace_stamp(ops, 7);
+      const int tix = threadIdx.x - 64;
+      constexpr int kThreads = 32 * kEpiWarps;
+      uint8_t* mine = smem + kq * 16384;
+      uint32_t peer[KSPLIT - 1];
+#pragma unroll
+      for (int p = 0; p < KSPLIT - 1; ++p) peer[p] = map_to_cta(smem_u32(mine), (uint32_t)((kq + 1 + p) % KSPLIT));
+      constexpr int kIter = 1024 / kThreads;
+      float4 rv[kIter][KSPLIT - 1];
+#pragma unroll
+      for (int i = 0; i < kIter; ++i)                 // all remote loads in flight before the first use
+#pragma unroll
+        for (int p = 0; p < KSPLIT - 1; ++p) rv[i][p] = ld_cluster_f4(peer[p] + (uint32_t)(tix + kThreads * i) * 16);
+#pragma unroll
+      for (int i = 0; i < kIter; ++i) {
+        const uint32_t off = (uint32_t)(tix + kThreads * i) * 16;
+        float4 sacc = *reinterpret_cast<const float4*>(mine + off);
+#pragma unroll
+        for (int p = 0; p < KSPLIT - 1; ++p) {
+          sacc.x += rv[i][p].x; sacc.y += rv[i][p].y; sacc.z += rv[i][p].z; sacc.w += rv[i][p].w;
+        }
+        *reinterpret_cast<float4*>(mine + off) = sacc;
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      if (threadIdx.x == 64) {
-        trace_stamp(ops, 8);
-        Epi::issue_stores(ep, smem, m0, n0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        trace_stamp(ops, 9);
+      Epi::apply_from_smem(ep, in_smem, out_smem, mine, tix & 127, tix >> 7, kEpiWarps / 4);
+      if (Epi::kOutBytes > 0) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 64) {
+          trace_stamp(ops, 8);
+          Epi::issue_stores(ep, out_smem, m0, n_epi);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          trace_stamp(ops, 9);
+        }
       }
     }
+    cluster_sync_all();                                              // peers are done reading my partials
   }
   tc_fence_before();
   __syncthreads();
@@ -228,10 +300,10 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, u
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows);
 
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4>
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1>
 cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t stream) {
-  using S = GemmSmem<BN, kStages, Epi>;
-  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps>;
+  using S = GemmSmem<BN, kStages, Epi, KSPLIT>;
+  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps, KSPLIT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -240,15 +312,23 @@ cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& 
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((ops.N + BN - 1) / BN, (ops.M + kBM - 1) / kBM);
+  cfg.gridDim = dim3(((ops.N + BN - 1) / BN) * KSPLIT, (ops.M + kBM - 1) / kBM);
   cfg.blockDim = dim3(64 + 32 * kEpiWarps);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (KSPLIT > 1) {
+    if (((ops.K + kBK - 1) / kBK) % KSPLIT != 0) return cudaErrorInvalidValue;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = KSPLIT;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, ops, ep);
 }
 
