@@ -103,6 +103,12 @@ int svb_eer_counts(const float* sim, int n_local, int Mv, int Nc, int speaker0, 
  * FAR, FRR; out[4..4+T) = FAR per threshold, out[4+T..4+2T) = FRR per threshold. */
 int svb_eer_finish(const int* cnt_all, const int* cnt_diag, int N, int Mv, int T, float* out, void* stream);
 
+/* Single-launch sweep for one GPU: per-speaker counts, integer totals (atomics) and the selection above, done by the
+ * last block.  scratch: 1 + 16T uint64 zeroed by the caller.  out[1] == -2: a total exceeded 2^24, so float32 partial
+ * sums are no longer exact -- call svb_eer_finish on the returned per-speaker counts instead. */
+int svb_eer_sweep(const float* sim, int N, int Mv, const float* thresholds, int T, int* cnt_all, int* cnt_diag,
+                  unsigned long long* scratch, float* out, void* stream);
+
 /* ---- d-vector extraction (dvector_create.py:48-52,98-99 and :55-73) ----------------------------------------------- */
 
 /* Sliding windows of a (nmels, Ttot) log-mel matrix (row pitch ldS) -> (W, win, nmels); win_start (W) int32 device. */

@@ -114,6 +114,147 @@ __global__ void eer_finish_kernel(const int* __restrict__ cnt_all, const int* __
   }
 }
 
+
+// Branch-free bucket search for T < 64 (thr padded with +inf up to 64 entries): fixed 6 steps, so the searches of
+// the many elements a lane holds are independent instruction streams the scheduler can interleave.
+__device__ __forceinline__ int bucket_of64(float v, const float* thr) {
+  int lo = 0;
+#pragma unroll
+  for (int step = 32; step >= 1; step >>= 1) {
+    const int c = lo + step;
+    if (v > thr[c - 1]) lo = c;
+  }
+  return lo;
+}
+
+// ---- single-launch sweep: one warp per speaker (all its float4 loads issued up front), integer atomics into the
+// ---- global totals, and the last block to finish reproduces the reference's float32 arithmetic.
+__device__ __forceinline__ void eer_scan(const float* far_s, const float* frr_s, int T, float* out) {
+  float diff = 1.0f, EER = 0.f, eFAR = 0.f, eFRR = 0.f;
+  int sel = -1;
+  for (int k = 0; k < T; ++k) {
+    const float d = fabsf(__fsub_rn(far_s[k], frr_s[k]));
+    if (diff > d) {
+      diff = d;
+      EER = __fdiv_rn(__fadd_rn(far_s[k], frr_s[k]), 2.0f);
+      sel = k; eFAR = far_s[k]; eFRR = frr_s[k];
+    }
+  }
+  out[0] = EER; out[1] = (float)sel; out[2] = eFAR; out[3] = eFRR;
+}
+
+constexpr int kSweepWarps = 4;
+constexpr int kBk = 64;           // bucket rows of the lane-private histogram (T + 1 <= 64 on this path)
+// scratch (zeroed by the host): [0] block ticket, then 8 replicas of the totals [8][2][T]: sum over speakers of
+// (cnt_all - cnt_diag) and of cnt_diag, accumulated with integer atomics (exact in any order).
+__global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float* __restrict__ sim, int N, int Mv, int Nc,
+                                                                     const float* __restrict__ thr_g, int T,
+                                                                     int* __restrict__ cnt_all, int* __restrict__ cnt_diag,
+                                                                     unsigned long long* __restrict__ scratch,
+                                                                     float* __restrict__ out) {
+  __shared__ float thr[kBk];
+  __shared__ int hist[kSweepWarps][kBk][32];      // lane-private columns: plain increments, no bank conflicts
+  __shared__ int hsum[kSweepWarps][2][kBk];
+  __shared__ float far_s[kMaxThr], frr_s[kMaxThr];
+  __shared__ int btot[2][kMaxThr];
+  __shared__ int last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < kBk; t += blockDim.x) {
+    thr[t] = t < T ? thr_g[t] : INFINITY;
+    btot[0][t] = 0; btot[1][t] = 0;
+  }
+  for (int bk = 0; bk <= T; ++bk) hist[warp][bk][lane] = 0;
+  for (int t = lane; t < kBk; t += 32) { hsum[warp][0][t] = 0; hsum[warp][1][t] = 0; }
+  __syncthreads();
+  const int i = blockIdx.x * kSweepWarps + warp;
+  if (i < N) {
+    const float* base = sim + (size_t)i * Mv * Nc;
+    const float t0 = thr[0];
+    const int n = Mv * Nc;
+    int (*h)[32] = hist[warp];
+    int* h_all = hsum[warp][0];
+    int* h_diag = hsum[warp][1];
+    if ((Nc & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(base);
+      const int n4 = n >> 2;
+      for (int q0 = 0; q0 < n4; q0 += 32 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int q = q0 + u * 32 + lane;
+          v[u] = q < n4 ? __ldg(b4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) atomicAdd(&h[bucket_of64(vv[e], thr)][lane], 1);   // lane-private: no contention
+        }
+      }
+    } else {
+      for (int idx = lane; idx < n; idx += 32) {
+        const float v = base[idx];
+        atomicAdd(&h[bucket_of64(v, thr)][lane], 1);
+      }
+    }
+    for (int m = lane; m < Mv; m += 32) {               // the diagonal column of this speaker's row block
+      const float v = base[(size_t)m * Nc + i];
+      if (v > t0) atomicAdd(&h_diag[bucket_of64(v, thr)], 1);
+    }
+    __syncwarp();
+    for (int bk = lane; bk <= T; bk += 32) {            // fold the 32 lane-private columns of each bucket
+      int tot = 0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) tot += h[bk][(l + lane) & 31];
+      h_all[bk] = tot;
+    }
+    __syncwarp();
+    for (int t = lane; t < T; t += 32) {                // count(sim > thr[t]) = sum_{bk > t} hist[bk]
+      int sa = 0, sd = 0;
+      for (int bk = t + 1; bk <= T; ++bk) { sa += h_all[bk]; sd += h_diag[bk]; }
+      cnt_all[(size_t)i * T + t] = sa;
+      cnt_diag[(size_t)i * T + t] = sd;
+      if (sa - sd) atomicAdd(&btot[0][t], sa - sd);
+      if (sd) atomicAdd(&btot[1][t], sd);
+    }
+  }
+  __syncthreads();
+  // integer atomics (exact, order-independent) into one of 8 replicas of the totals to spread same-address traffic
+  unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x & 7) * 2 * T;
+  for (int t = threadIdx.x; t < 2 * T; t += blockDim.x) {
+    const int v = btot[t / T][t % T];
+    if (v) atomicAdd(&part[t], (unsigned long long)v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&scratch[0], 1ULL) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  bool exact = true;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    unsigned long long fa = 0, di = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      fa += __ldcg(scratch + 1 + (size_t)r * 2 * T + t);
+      di += __ldcg(scratch + 1 + (size_t)r * 2 * T + T + t);
+    }
+    const unsigned long long fr = (unsigned long long)N * Mv - di;
+    // the reference adds float32 terms left to right; integer-valued partial sums are exact below 2^24
+    if (fa > (1ULL << 24) || fr > (1ULL << 24)) exact = false;
+    const float mv = (float)Mv;
+    const float FAR = __fdiv_rn(__fdiv_rn(__fdiv_rn((float)fa, (float)(N - 1.0)), mv), (float)N);
+    const float FRR = __fdiv_rn(__fdiv_rn((float)fr, mv), (float)N);
+    far_s[t] = FAR; frr_s[t] = FRR;
+    out[4 + t] = FAR; out[4 + T + t] = FRR;
+  }
+  const int all_exact = __syncthreads_and(exact ? 1 : 0);
+  if (threadIdx.x == 0) {
+    eer_scan(far_s, frr_s, T, out);
+    if (!all_exact) out[1] = -2.0f;                     // caller falls back to the sequential float32 kernel
+  }
+}
+
 }  // namespace svb
 using namespace svb;
 
@@ -136,5 +277,20 @@ extern "C" int svb_eer_finish(const int* cnt_all, const int* cnt_diag, int N, in
   eer_finish_kernel<<<1, kMaxThr, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cnt_all, cnt_diag, N, Mv, T, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("svb_eer_finish", e); return SVB_ERR_CUDA; }
+  return SVB_OK;
+}
+
+/* One launch: per-speaker counts + totals + the reference's float32 FAR/FRR/EER selection.  scratch: 1 + 16T uint64 zeroed by the caller.  out as svb_eer_finish; out[1] == -2 means a count exceeded 2^24 (float32 partial sums no
+ * longer exact): call svb_eer_finish on the per-speaker counts instead. */
+extern "C" int svb_eer_sweep(const float* sim, int N, int Mv, const float* thresholds, int T, int* cnt_all,
+                             int* cnt_diag, unsigned long long* scratch, float* out, void* stream) {
+  if (!sim || !thresholds || !cnt_all || !cnt_diag || !scratch || !out || N < 2 || Mv < 1 || T < 1 || T >= kBk) {
+    set_error("svb_eer_sweep: bad argument (T must be < 64)", cudaSuccess);
+    return SVB_ERR_ARG;
+  }
+  eer_sweep_kernel<<<(N + kSweepWarps - 1) / kSweepWarps, 32 * kSweepWarps, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sim, N, Mv, N, thresholds, T, cnt_all, cnt_diag, scratch, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("svb_eer_sweep", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }

@@ -28,8 +28,6 @@ constexpr float kCosBias = 1e-6f;   // utils.py:114
 constexpr float kLogBias = 1e-6f;   // utils.py:129
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kKC = 8;              // centroids per phase-C tile
-constexpr int kDT = 32;             // dims per phase-C tile
 
 struct Ge2eArgs {
   const float* E;        // [N, M, D]
@@ -40,6 +38,7 @@ struct Ge2eArgs {
   const float* gscale;   // device scalar multiplying all gradients (upstream dL) or null (= 1)
   int N, M, D, Nc;
   int need_grad;
+  int psplit, prows;     // P = A_off^T E^ is accumulated over psplit slices of prows embedding rows
   // outputs (nullable)
   float* cos_out;        // [N, M, Nc]  cos + 1e-6
   float* per_out;        // [N, M]
@@ -60,7 +59,8 @@ struct Ge2eArgs {
   float* Aoff;           // [N*M, Nc] upstream dL/dcos with the diagonal zeroed
   float* adiag;          // [N*M]
   float* rowstat;        // [3, N*M]: per-row loss, dw, db contributions
-  float* dC;             // [Nc, D]
+  float* dC;             // [Nc, D]  P = A_off^T E^ (numerator of the centroid gradient)
+  float* R;              // [N*M, D] A_off C^
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -87,33 +87,37 @@ __device__ float block_sum(float v, float* red) {
 
 // ---------------------------------------------------------------------------------------------- phase A
 __device__ void phase_a(const Ge2eArgs& a, float* smem) {
-  float* s = smem;              // [D]
-  float* red = smem + a.D;      // [kWarps]
+  float* s = smem;                       // [D]
+  float* red = smem + a.D;               // [kWarps]
+  float* rows = red + kWarps;            // [M, D] the speaker's embeddings (one coalesced batch of loads)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float invM = 1.0f / (float)a.M;
-  const float invM1 = 1.0f / (float)(a.M - 1);
+  const int M = a.M, D = a.D;
+  const float invM = 1.0f / (float)M;
+  const float invM1 = 1.0f / (float)(M - 1);
   for (int j = blockIdx.x; j < a.N; j += gridDim.x) {
-    const float* Ej = a.E + (size_t)j * a.M * a.D;
+    const float* Ej = a.E + (size_t)j * M * D;
+    for (int i = threadIdx.x; i < M * D; i += kThreads) rows[i] = Ej[i];
+    __syncthreads();
     float cc = 0.f;
-    for (int d = threadIdx.x; d < a.D; d += kThreads) {
+    for (int d = threadIdx.x; d < D; d += kThreads) {
       float acc = 0.f;
-      for (int m = 0; m < a.M; ++m) acc += Ej[(size_t)m * a.D + d];
+      for (int m = 0; m < M; ++m) acc += rows[m * D + d];
       s[d] = acc;
-      a.Ssum[(size_t)j * a.D + d] = acc;
+      a.Ssum[(size_t)j * D + d] = acc;
       const float c = acc * invM;
       cc += c * c;
     }
     if (!a.Cext) {
       cc = block_sum(cc, red);
       const float inc = 1.0f / fmaxf(sqrtf(cc), kCosEps);
-      for (int d = threadIdx.x; d < a.D; d += kThreads) a.Chat[(size_t)j * a.D + d] = s[d] * invM * inc;
+      for (int d = threadIdx.x; d < D; d += kThreads) a.Chat[(size_t)j * D + d] = s[d] * invM * inc;
       if (threadIdx.x == 0) a.inv_nc[j] = inc;
     }
     __syncthreads();
-    for (int m = warp; m < a.M; m += kWarps) {
-      const float* e = Ej + (size_t)m * a.D;
+    for (int m = warp; m < M; m += kWarps) {
+      const float* e = rows + m * D;
       float ee = 0.f, uu = 0.f, eu = 0.f;
-      for (int d = lane; d < a.D; d += 32) {
+      for (int d = lane; d < D; d += 32) {
         const float x = e[d];
         const float u = (s[d] - x) * invM1;
         ee += x * x; uu += u * u; eu += x * u;
@@ -121,8 +125,8 @@ __device__ void phase_a(const Ge2eArgs& a, float* smem) {
       ee = warp_sum(ee); uu = warp_sum(uu); eu = warp_sum(eu);
       const float ine = 1.0f / fmaxf(sqrtf(ee), kCosEps);
       const float inu = 1.0f / fmaxf(sqrtf(uu), kCosEps);
-      const size_t row = (size_t)j * a.M + m;
-      for (int d = lane; d < a.D; d += 32) a.Ehat[row * a.D + d] = e[d] * ine;
+      const size_t row = (size_t)j * M + m;
+      for (int d = lane; d < D; d += 32) a.Ehat[row * D + d] = e[d] * ine;
       if (lane == 0) {
         a.inv_ne[row] = ine;
         a.inv_nu[row] = inu;
@@ -144,215 +148,246 @@ __device__ void phase_a(const Ge2eArgs& a, float* smem) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------- phase B
-__device__ void phase_b(const Ge2eArgs& a, float* smem) {
-  const int M = a.M, D = a.D, Nc = a.Nc;
-  float* rows = smem;                       // [M, D] unit rows e^
-  float* tile = rows + (size_t)M * D;       // [M, Nc] cos, then A_off
-  float* rstat = tile + (size_t)M * Nc;     // [M, 4]: r_row, a_diag, (unused)
+// ---------------------------------------------------------------------------------------------- tiled fp32 GEMM
+// C[m, n] = sum_k A(m, k) * B(n, k) for one 64 x 64 tile; A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]
+// (one of each stride pair is 1).  256 threads, 4 x 4 register tile each, K staged 16 at a time in shared memory.
+constexpr int kTM = 64, kTN = 64, kTK = 32;
+constexpr int kLd = kTM * kTK / kThreads;        // elements per thread per operand per K chunk (8)
+__device__ __forceinline__ void tile_fetch(const float* __restrict__ P, int64_t sr, int64_t sk, int R, int K, int r0,
+                                           int k0, float (&v)[kLd]) {
+#pragma unroll
+  for (int i = 0; i < kLd; ++i) {
+    const int e = threadIdx.x + i * kThreads;
+    int r, k;
+    if (sk == 1) { k = e % kTK; r = e / kTK; } else { r = e % kTM; k = e / kTM; }
+    const int gr = r0 + r, gk = k0 + k;
+    v[i] = (gr < R && gk < K) ? P[gr * sr + gk * sk] : 0.f;
+  }
+}
+__device__ __forceinline__ void tile_stash(float (*S)[kTM + 4], int64_t sk, const float (&v)[kLd]) {
+#pragma unroll
+  for (int i = 0; i < kLd; ++i) {
+    const int e = threadIdx.x + i * kThreads;
+    int r, k;
+    if (sk == 1) { k = e % kTK; r = e / kTK; } else { r = e % kTM; k = e / kTM; }
+    S[k][r] = v[i];
+  }
+}
+__device__ void gemm_tile_64(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B,
+                             int64_t sbn, int64_t sbk, float* __restrict__ C, int64_t ldc, int M, int N, int K, int m0,
+                             int n0, float* smem) {
+  float (*As)[kTM + 4] = reinterpret_cast<float (*)[kTM + 4]>(smem);                       // [kTK][kTM+4]
+  float (*Bs)[kTN + 4] = reinterpret_cast<float (*)[kTN + 4]>(smem + kTK * (kTM + 4));     // [kTK][kTN+4]
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float va[kLd], vb[kLd];
+  tile_fetch(A, sam, sak, M, K, m0, 0, va);
+  tile_fetch(B, sbn, sbk, N, K, n0, 0, vb);
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+    __syncthreads();                                   // previous chunk fully consumed
+    tile_stash(As, sak, va);
+    tile_stash(Bs, sbk, vb);
+    __syncthreads();
+    if (k0 + kTK < K) {                                // next chunk's loads fly while this one is multiplied
+      tile_fetch(A, sam, sak, M, K, m0, k0 + kTK, va);
+      tile_fetch(B, sbn, sbk, N, K, n0, k0 + kTK, vb);
+    }
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + 4 * ty + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + 4 * tx + j;
+      if (gn < N) C[gm * ldc + gn] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- phase B1: cosine GEMM
+__device__ void phase_b1(const Ge2eArgs& a, float* smem) {
+  const int NM = a.N * a.M;
+  const int mt = (NM + kTM - 1) / kTM, nt = (a.Nc + kTN - 1) / kTN;
+  for (int tix = blockIdx.x; tix < mt * nt; tix += gridDim.x)
+    gemm_tile_64(a.Ehat, a.D, 1, a.Chat, a.D, 1, a.cosm, a.Nc, NM, a.Nc, a.D, (tix / nt) * kTM, (tix % nt) * kTN, smem);
+}
+
+// ---------------------------------------------------------------------------------------------- phase B2: row softmax
+// one warp per embedding row: diagonal overwrite, S = w cos + b, stable log-sum-exp, G, A = w G (diag split off)
+__device__ void phase_b2(const Ge2eArgs& a) {
+  const int M = a.M, Nc = a.Nc, NM = a.N * a.M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float w = a.w ? *a.w : 0.f, b = a.b ? *a.b : 0.f;
-  const float invM1 = 1.0f / (float)(M - 1);
-  for (int j = blockIdx.x; j < a.N; j += gridDim.x) {
-    const size_t row0 = (size_t)j * M;
-    for (int i = threadIdx.x; i < M * D; i += kThreads) rows[i] = a.Ehat[row0 * D + i];
-    __syncthreads();
-    // cos[m, k] = e^_m . c^_k : one warp per centroid, lanes over d, rows from shared memory
-    for (int k = warp; k < Nc; k += kWarps) {
-      const float* c = a.Chat + (size_t)k * D;
-      for (int m0 = 0; m0 < M; m0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-        for (int d = lane; d < D; d += 32) {
-          const float cv = c[d];
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (m0 + r < M) acc[r] += cv * rows[(size_t)(m0 + r) * D + d];
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float v = warp_sum(acc[r]);
-          if (lane == 0 && m0 + r < M) tile[(size_t)(m0 + r) * Nc + k] = v;
-        }
-      }
-    }
-    __syncthreads();
-    // per-row softmax contrast: one warp per row
-    for (int m = warp; m < M; m += kWarps) {
-      const size_t row = row0 + m;
-      float* t = tile + (size_t)m * Nc;
-      const float cd = a.cosd[row];
-      if (lane == 0 && j < Nc) t[j] = cd;          // diagonal overwrite (utils.py:113)
-      __syncwarp();
+  for (int row = blockIdx.x * kWarps + warp; row < NM; row += gridDim.x * kWarps) {
+    const int j = row / M;
+    float* t = a.cosm + (size_t)row * Nc;
+    const float cd = a.cosd[row];
+    if (lane == 0 && j < Nc) t[j] = cd;                 // diagonal overwrite (utils.py:113)
+    __syncwarp();
+    if (a.cos_out)
+      for (int k = lane; k < Nc; k += 32) a.cos_out[(size_t)row * Nc + k] = t[k] + kCosBias;
+    if (a.w) {
+      float mx = -INFINITY;
+      for (int k = lane; k < Nc; k += 32) mx = fmaxf(mx, w * (t[k] + kCosBias) + b);
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int k = lane; k < Nc; k += 32) se += expf(w * (t[k] + kCosBias) + b - mx);
+      se = warp_sum(se);
+      // log(sum exp S + 1e-6) = mx + log(se + 1e-6 e^{-mx})  (reference has no max-subtraction: same value)
+      const float tiny = kLogBias * expf(-mx);
+      const float den = se + tiny;
+      const float per = -(w * (cd + kCosBias) + b) + mx + logf(den);
+      const float inv_den = 1.0f / den;
+      float dwp = 0.f, ad = 0.f;
       for (int k = lane; k < Nc; k += 32) {
         const float c0 = t[k];
-        a.cosm[row * Nc + k] = c0;
-        if (a.cos_out) a.cos_out[row * Nc + k] = c0 + kCosBias;
+        float g = expf(w * (c0 + kCosBias) + b - mx) * inv_den;
+        if (k == j) g -= 1.0f;
+        dwp += g * (c0 + kCosBias);
+        const float A = w * g;
+        if (k == j) ad = A;
+        a.Aoff[(size_t)row * Nc + k] = (k == j) ? 0.f : A;
       }
-      if (a.w) {
-        float mx = -INFINITY;
-        for (int k = lane; k < Nc; k += 32) mx = fmaxf(mx, w * (t[k] + kCosBias) + b);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int k = lane; k < Nc; k += 32) se += expf(w * (t[k] + kCosBias) + b - mx);
-        se = warp_sum(se);
-        // log(sum exp S + 1e-6) = mx + log(se + 1e-6 e^{-mx})  (reference has no max-subtraction: same value)
-        const float tiny = kLogBias * expf(-mx);
-        const float den = se + tiny;
-        const float sdiag = w * (cd + kCosBias) + b;
-        const float per = -sdiag + mx + logf(den);
-        const float inv_den = 1.0f / den;
-        float dwp = 0.f, rr = 0.f, ad = 0.f;
-        for (int k = lane; k < Nc; k += 32) {
-          const float c0 = t[k];
-          float g = expf(w * (c0 + kCosBias) + b - mx) * inv_den;
-          if (k == j) g -= 1.0f;
-          dwp += g * (c0 + kCosBias);
-          const float A = w * g;
-          float ao = A;
-          if (k == j) { ad = A; ao = 0.f; }
-          rr += ao * c0;
-          t[k] = ao;
-          a.Aoff[row * Nc + k] = ao;
-        }
-        dwp = warp_sum(dwp); rr = warp_sum(rr); ad = warp_sum(ad);
-        if (lane == 0) {
-          const int NM = a.N * M;
-          a.rowstat[row] = per;
-          a.rowstat[NM + row] = dwp;
-          a.rowstat[2 * NM + row] = -tiny * inv_den;     // sum_k G = -1e-6/den exactly
-          if (a.per_out) a.per_out[row] = per;
-          a.adiag[row] = ad;
-          rstat[m * 4 + 0] = rr;
-          rstat[m * 4 + 1] = ad;
-        }
-      } else if (a.dcos) {   // get_cossim backward: upstream gradient given
-        float rr = 0.f, ad = 0.f;
-        for (int k = lane; k < Nc; k += 32) {
-          const float c0 = t[k];
-          const float A = a.dcos[row * Nc + k];
-          float ao = A;
-          if (k == j) { ad = A; ao = 0.f; }
-          rr += ao * c0;
-          t[k] = ao;
-          a.Aoff[row * Nc + k] = ao;
-        }
-        rr = warp_sum(rr); ad = warp_sum(ad);
-        if (lane == 0) {
-          a.adiag[row] = ad;
-          rstat[m * 4 + 0] = rr;
-          rstat[m * 4 + 1] = ad;
-        }
+      dwp = warp_sum(dwp); ad = warp_sum(ad);
+      if (lane == 0) {
+        a.rowstat[row] = per;
+        a.rowstat[NM + row] = dwp;
+        a.rowstat[2 * NM + row] = -tiny * inv_den;     // sum_k G = -1e-6/den exactly
+        if (a.per_out) a.per_out[row] = per;
+        a.adiag[row] = ad;
       }
+    } else if (a.dcos) {   // get_cossim backward: upstream gradient given
+      float ad = 0.f;
+      for (int k = lane; k < Nc; k += 32) {
+        const float A = a.dcos[(size_t)row * Nc + k];
+        if (k == j) ad = A;
+        a.Aoff[(size_t)row * Nc + k] = (k == j) ? 0.f : A;
+      }
+      ad = warp_sum(ad);
+      if (lane == 0) a.adiag[row] = ad;
     }
-    __syncthreads();
-    if (a.need_grad) {
-      // row-local gradient: thread per dim, 8 rows of accumulators
-      const float* sj = a.Ssum + (size_t)j * D;
-      for (int d = threadIdx.x; d < D; d += kThreads) {
-        for (int m0 = 0; m0 < M; m0 += 8) {
-          float acc[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-          for (int k = 0; k < Nc; ++k) {
-            const float cv = a.Chat[(size_t)k * D + d];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-              if (m0 + r < M) acc[r] += tile[(size_t)(m0 + r) * Nc + k] * cv;
-          }
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int m = m0 + r;
-            if (m < M) {
-              const size_t row = row0 + m;
-              const float eh = rows[(size_t)m * D + d];
-              const float ine = a.inv_ne[row];
-              const float uh = (sj[d] - a.E[row * D + d]) * invM1 * a.inv_nu[row];
-              const float cd = a.cosd[row];
-              a.dE[row * D + d] = (acc[r] - rstat[m * 4 + 0] * eh) * ine + rstat[m * 4 + 1] * (uh - cd * eh) * ine;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
   }
 }
 
-// ---------------------------------------------------------------------------------------------- phase C
+// ---------------------------------------------------------------------------------------------- phase C: two GEMMs
+// R[row, d] = sum_k A_off[row, k] c^_k[d]   and   P[k, d] = sum_row A_off[row, k] e^_row[d]
 __device__ void phase_c(const Ge2eArgs& a, float* smem) {
-  float* red = smem;                       // [kWarps][kKC][kDT]
-  float* qred = red + kWarps * kKC * kDT;  // [kWarps][kKC]
-  const int D = a.D, Nc = a.Nc, NM = a.N * a.M;
-  const int ktiles = (Nc + kKC - 1) / kKC, dtiles = (D + kDT - 1) / kDT;
-  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = row group, lane = dim
-  for (int tix = blockIdx.x; tix < ktiles * dtiles; tix += gridDim.x) {
-    const int k0 = (tix / dtiles) * kKC, d = (tix % dtiles) * kDT + lane;
-    float acc[kKC];
-#pragma unroll
-    for (int i = 0; i < kKC; ++i) acc[i] = 0.f;
-    float q = 0.f;
-    for (int row = rg; row < NM; row += kWarps) {
-      const float eh = d < D ? a.Ehat[(size_t)row * D + d] : 0.f;
-      const float* ao = a.Aoff + (size_t)row * Nc + k0;
-#pragma unroll
-      for (int i = 0; i < kKC; ++i)
-        if (k0 + i < Nc) acc[i] += ao[i] * eh;
-      if (lane < kKC && k0 + lane < Nc) q += ao[lane] * a.cosm[(size_t)row * Nc + k0 + lane];
+  const int NM = a.N * a.M, D = a.D, Nc = a.Nc;
+  const int dt = (D + kTN - 1) / kTN;
+  const int rt = ((NM + kTM - 1) / kTM) * dt;
+  const int pk = (Nc + kTM - 1) / kTM;
+  const int pt = a.psplit * pk * dt;                    // P is reduced over `psplit` slices of `prows` rows each
+  for (int tix = blockIdx.x; tix < rt + pt; tix += gridDim.x) {
+    if (tix < pt) {
+      const int sl = tix / (pk * dt), u = tix % (pk * dt);
+      const int r0 = sl * a.prows;
+      const int rows = NM - r0 < a.prows ? NM - r0 : a.prows;
+      gemm_tile_64(a.Aoff + (size_t)r0 * Nc, 1, Nc, a.Ehat + (size_t)r0 * D, 1, D, a.dC + (size_t)sl * Nc * D, D, Nc, D,
+                   rows, (u / dt) * kTM, (u % dt) * kTN, smem);
+    } else {
+      const int u = tix - pt;
+      gemm_tile_64(a.Aoff, Nc, 1, a.Chat, 1, D, a.R, D, NM, D, Nc, (u / dt) * kTM, (u % dt) * kTN, smem);
     }
-#pragma unroll
-    for (int i = 0; i < kKC; ++i) red[(rg * kKC + i) * kDT + lane] = acc[i];
-    if (lane < kKC) qred[rg * kKC + lane] = q;
-    __syncthreads();
-    {
-      const int i = threadIdx.x >> 5;      // kWarps == kKC: warp i finishes centroid k0 + i
-      const int k = k0 + i;
-      if (k < Nc && d < D) {
-        float p = 0.f, qq = 0.f;
-#pragma unroll
-        for (int g = 0; g < kWarps; ++g) { p += red[(g * kKC + i) * kDT + lane]; qq += qred[g * kKC + i]; }
-        a.dC[(size_t)k * D + d] = (p - qq * a.Chat[(size_t)k * D + d]) * a.inv_nc[k];
-      }
-    }
-    __syncthreads();
   }
 }
-static_assert(kWarps == kKC, "phase C maps one warp per centroid of the tile");
 
 // ---------------------------------------------------------------------------------------------- phase D
+// per speaker j: dC_j = (P_j - (P_j.c^_j) c^_j)/|c_j|;  per row: r = R.e^ (= sum_k A_off cos, since cos = e^.c^);
+// dE = (R - r e^)/|e| + a (u^ - cosd e^)/|e| + dC_j/M + (sum_m dU_m - dU_i)/(M-1)
+__device__ float sum_slices(const float* p, size_t stride, int n) {
+  float v = 0.f;
+  for (int i = 0; i < n; ++i) v += p[(size_t)i * stride];
+  return v;
+}
 __device__ void phase_d(const Ge2eArgs& a, float* smem) {
-  float* red = smem;
   const int M = a.M, D = a.D, NM = a.N * a.M;
+  float* red = smem;                 // [kWarps]
+  float* rr = red + kWarps;          // [M]
+  float* sc = rr + M;                // [4, M] inv_ne, inv_nu, cosd, adiag
+  float* vec = sc + 4 * M;           // [3, D] P_j, c^_j, s_j
+  float* rE = vec + 3 * D;           // [M, D] e
+  float* rH = rE + (size_t)M * D;    // [M, D] e^
+  float* rR = rH + (size_t)M * D;    // [M, D] R
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float gs = a.gscale ? *a.gscale : 1.0f;
   if (a.need_grad) {
     const float invM = 1.0f / (float)M, invM1 = 1.0f / (float)(M - 1);
+    const size_t pstride = (size_t)a.Nc * D;
     for (int j = blockIdx.x; j < a.N; j += gridDim.x) {
       const size_t row0 = (size_t)j * M;
+      // one coalesced batch of independent loads per speaker, everything else from shared memory
+      for (int i = threadIdx.x; i < M * D; i += kThreads) {
+        rE[i] = a.E[row0 * D + i];
+        rH[i] = a.Ehat[row0 * D + i];
+        rR[i] = a.R[row0 * D + i];
+      }
       for (int d = threadIdx.x; d < D; d += kThreads) {
-        const float sj = a.Ssum[(size_t)j * D + d];
+        vec[d] = a.Cext ? 0.f : sum_slices(a.dC + (size_t)j * D + d, pstride, a.psplit);
+        vec[D + d] = a.Cext ? 0.f : a.Chat[(size_t)j * D + d];
+        vec[2 * D + d] = a.Ssum[(size_t)j * D + d];
+      }
+      for (int m = threadIdx.x; m < M; m += kThreads) {
+        sc[m] = a.inv_ne[row0 + m]; sc[M + m] = a.inv_nu[row0 + m];
+        sc[2 * M + m] = a.cosd[row0 + m]; sc[3 * M + m] = a.adiag[row0 + m];
+      }
+      __syncthreads();
+      float q = 0.f;
+      for (int d = threadIdx.x; d < D; d += kThreads) q += vec[d] * vec[D + d];
+      q = block_sum(q, red);
+      for (int m = warp; m < M; m += kWarps) {
+        float r = 0.f;
+        for (int d = lane; d < D; d += 32) r += rR[m * D + d] * rH[m * D + d];
+        r = warp_sum(r);
+        if (lane == 0) rr[m] = r;
+      }
+      __syncthreads();
+      const float incj = a.Cext ? 0.f : a.inv_nc[j];
+      for (int d = threadIdx.x; d < D; d += kThreads) {
+        const float sj = vec[2 * D + d];
         float sumdu = 0.f;
         for (int m = 0; m < M; ++m) {
-          const size_t row = row0 + m;
-          const float eh = a.Ehat[row * D + d];
-          const float inu = a.inv_nu[row];
-          const float uh = (sj - a.E[row * D + d]) * invM1 * inu;
-          sumdu += a.adiag[row] * (eh - a.cosd[row] * uh) * inu;
+          const float eh = rH[m * D + d], inu = sc[M + m];
+          const float uh = (sj - rE[m * D + d]) * invM1 * inu;
+          sumdu += sc[3 * M + m] * (eh - sc[2 * M + m] * uh) * inu;
         }
-        const float dc = (a.Cext == nullptr) ? a.dC[(size_t)j * D + d] * invM : 0.f;
+        const float dc = (vec[d] - q * vec[D + d]) * incj * invM;
         for (int m = 0; m < M; ++m) {
-          const size_t row = row0 + m;
-          const float eh = a.Ehat[row * D + d];
-          const float inu = a.inv_nu[row];
-          const float uh = (sj - a.E[row * D + d]) * invM1 * inu;
-          const float du = a.adiag[row] * (eh - a.cosd[row] * uh) * inu;
-          a.dE[row * D + d] = gs * (a.dE[row * D + d] + dc + (sumdu - du) * invM1);
+          const float eh = rH[m * D + d];
+          const float ine = sc[m], inu = sc[M + m], cd = sc[2 * M + m], ad = sc[3 * M + m];
+          const float uh = (sj - rE[m * D + d]) * invM1 * inu;
+          const float du = ad * (eh - cd * uh) * inu;
+          const float local = (rR[m * D + d] - rr[m] * eh) * ine + ad * (uh - cd * eh) * ine;
+          a.dE[(row0 + m) * D + d] = gs * (local + dc + (sumdu - du) * invM1);
         }
       }
+      __syncthreads();
     }
-    if (a.Cext && a.dCext) {
-      for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < (size_t)a.Nc * D; i += (size_t)gridDim.x * kThreads)
-        a.dCext[i] = gs * a.dC[i];
+    if (a.Cext && a.dCext) {    // gradient w.r.t. foreign centroids: (P_k - (P_k.c^_k) c^_k)/|c_k|, one warp per k
+      for (int k = blockIdx.x * kWarps + warp; k < a.Nc; k += gridDim.x * kWarps) {
+        float q = 0.f;
+        const size_t pstr = (size_t)a.Nc * D;
+        for (int d = lane; d < D; d += 32) q += sum_slices(a.dC + (size_t)k * D + d, pstr, a.psplit) * a.Chat[(size_t)k * D + d];
+        q = warp_sum(q);
+        for (int d = lane; d < D; d += 32)
+          a.dCext[(size_t)k * D + d] = gs * (sum_slices(a.dC + (size_t)k * D + d, pstr, a.psplit) - q * a.Chat[(size_t)k * D + d]) * a.inv_nc[k];
+      }
     }
   }
   if (blockIdx.x == 0 && a.w) {
@@ -374,7 +409,9 @@ __global__ void __launch_bounds__(kThreads) ge2e_fused_kernel(const Ge2eArgs a) 
   cg::grid_group grid = cg::this_grid();
   phase_a(a, smem);
   grid.sync();
-  phase_b(a, smem);
+  phase_b1(a, smem);
+  grid.sync();
+  phase_b2(a);
   if (a.need_grad) {
     grid.sync();
     phase_c(a, smem);
@@ -385,8 +422,9 @@ __global__ void __launch_bounds__(kThreads) ge2e_fused_kernel(const Ge2eArgs a) 
 __global__ void __launch_bounds__(kThreads) ge2e_phase_kernel(const Ge2eArgs a, int phase) {
   extern __shared__ float smem[];
   if (phase == 0) phase_a(a, smem);
-  else if (phase == 1) phase_b(a, smem);
-  else if (phase == 2) phase_c(a, smem);
+  else if (phase == 1) phase_b1(a, smem);
+  else if (phase == 2) phase_b2(a);
+  else if (phase == 3) phase_c(a, smem);
   else phase_d(a, smem);
 }
 
@@ -394,20 +432,26 @@ static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 static size_t carve(Ge2eArgs& a, char* base) {
   const size_t NM = (size_t)a.N * a.M, D = a.D, Nc = a.Nc;
+  {   // <= 16 slices, each a multiple of 64 rows
+    int rows = (int)((NM + 15) / 16);
+    rows = ((rows + 63) / 64) * 64;
+    a.prows = rows;
+    a.psplit = (int)((NM + rows - 1) / rows);
+  }
   size_t off = 0;
   auto take = [&](size_t nfloats) { float* p = base ? reinterpret_cast<float*>(base + off) : nullptr; off += align_up(nfloats * 4); return p; };
   a.Ehat = take(NM * D); a.Chat = take(Nc * D); a.Ssum = take((size_t)a.N * D);
   a.inv_ne = take(NM); a.inv_nu = take(NM); a.cosd = take(NM); a.inv_nc = take(Nc);
-  a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take(Nc * D);
+  a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take((size_t)a.psplit * Nc * D); a.R = take(NM * D);
   return off;
 }
 
 static size_t smem_bytes(const Ge2eArgs& a) {
-  size_t pa = (size_t)a.D + kWarps;
-  size_t pb = (size_t)a.M * a.D + (size_t)a.M * a.Nc + (size_t)a.M * 4;
-  size_t pc = (size_t)kWarps * kKC * kDT + kWarps * kKC;
-  size_t m = pa > pb ? pa : pb;
-  m = m > pc ? m : pc;
+  size_t pa = (size_t)a.D + kWarps + (size_t)a.M * a.D;
+  size_t pg = (size_t)kTK * (kTM + 4) + (size_t)kTK * (kTN + 4);
+  size_t pd = (size_t)kWarps + 5 * (size_t)a.M + 3 * (size_t)a.D + 3 * (size_t)a.M * a.D;
+  size_t m = pa > pg ? pa : pg;
+  m = m > pd ? m : pd;
   return m * sizeof(float);
 }
 
@@ -438,7 +482,7 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   a.cos_out = cos_out; a.per_out = per_out; a.loss_out = loss_out; a.dE = dE; a.dCext = dCext; a.dw = dw; a.db = db;
   if (carve(a, static_cast<char*>(workspace)) > workspace_bytes) { set_error("svb_ge2e: workspace too small", cudaSuccess); return SVB_ERR_ARG; }
   const size_t smem = smem_bytes(a);
-  if (smem > 200 * 1024) { set_error("svb_ge2e: M*(D+Nc) too large for one CTA's shared memory", cudaSuccess); return SVB_ERR_UNSUPPORTED; }
+  if (smem > 200 * 1024) { set_error("svb_ge2e: M*D too large for one CTA's shared memory", cudaSuccess); return SVB_ERR_UNSUPPORTED; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static int max_smem_set = 0, num_sms = 0;
   if (!num_sms) {
@@ -452,21 +496,30 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
     if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
     max_smem_set = (int)smem;
   }
-  const int ctiles = ((Nc + kKC - 1) / kKC) * ((D + kDT - 1) / kDT);
-  int want = N > ctiles ? N : ctiles;
+  const int NMr = N * M;
+  const int dtl = (D + kTN - 1) / kTN;
+  const int b1tiles = ((NMr + kTM - 1) / kTM) * ((Nc + kTN - 1) / kTN);
+  const int ctiles = (((NMr + kTM - 1) / kTM) + a.psplit * ((Nc + kTM - 1) / kTM)) * dtl;
+  const int b2blocks = (NMr + kWarps - 1) / kWarps;
+  int want = N;
+  if (b1tiles > want) want = b1tiles;
+  if (ctiles > want && a.need_grad) want = ctiles;
+  if (b2blocks > want) want = b2blocks;
   if (fused) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, kThreads, smem);
     if (per_sm < 1) { set_error("svb_ge2e: kernel does not fit", cudaSuccess); return SVB_ERR_UNSUPPORTED; }
+    if (per_sm > 4) per_sm = 4;
     int grid = want < per_sm * num_sms ? want : per_sm * num_sms;
     void* params[] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)ge2e_fused_kernel, dim3(grid), dim3(kThreads), params, smem, s);
     if (e != cudaSuccess) { set_error("svb_ge2e: cooperative launch", e); return SVB_ERR_CUDA; }
   } else {
     ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 0);
-    ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 1);
-    if (a.need_grad) ge2e_phase_kernel<<<ctiles, kThreads, smem, s>>>(a, 2);
-    ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 3);
+    ge2e_phase_kernel<<<b1tiles, kThreads, smem, s>>>(a, 1);
+    ge2e_phase_kernel<<<b2blocks, kThreads, smem, s>>>(a, 2);
+    if (a.need_grad) ge2e_phase_kernel<<<ctiles, kThreads, smem, s>>>(a, 3);
+    ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 4);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("svb_ge2e: launch", e); return SVB_ERR_CUDA; }
   }

@@ -27,8 +27,14 @@ def eer_sweep(sim_matrix, thresholds=None):
     with torch.cuda.device(ops._dev()):
         sim = ops._stage(sim_matrix.detach(), torch.float32)
         thr = _thresholds_f32(sim.device, thresholds)
-        ca, cd = ops.eer_counts(sim, thr)
-        out = ops.eer_finish(ca, cd, sim.shape[1]).cpu()
+        if sim.shape[0] == sim.shape[2] and sim.shape[0] >= 2 and len(thresholds) < 64:
+            out_d, ca, cd = ops.eer_sweep_fused(sim, thr)
+            out = out_d.cpu()
+            if int(out[1]) == -2:                       # totals beyond 2^24: sequential float32 emulation
+                out = ops.eer_finish(ca, cd, sim.shape[1]).cpu()
+        else:
+            ca, cd = ops.eer_counts(sim, thr)
+            out = ops.eer_finish(ca, cd, sim.shape[1]).cpu()
     sel = int(out[1])
     if sel < 0:
         return 0, 0, 0, 0

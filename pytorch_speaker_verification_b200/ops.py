@@ -263,6 +263,19 @@ def eer_counts(sim, thresholds_f32, speaker0=0):
     return ca, cd
 
 
+def eer_sweep_fused(sim, thresholds_f32):
+    """One launch: (out[4 + 2T], cnt_all, cnt_diag); out[1] == -2 asks for the sequential eer_finish."""
+    N, Mv, Nc = (int(s) for s in sim.shape)
+    T = int(thresholds_f32.numel())
+    ca = torch.empty(N, T, dtype=torch.int32, device=sim.device)
+    cd = torch.empty(N, T, dtype=torch.int32, device=sim.device)
+    scratch = torch.zeros(1 + 16 * T, dtype=torch.int64, device=sim.device)
+    out = torch.empty(4 + 2 * T, dtype=torch.float32, device=sim.device)
+    check(_lib.lib().svb_eer_sweep(ptr(sim), N, Mv, ptr(thresholds_f32), T, ptr(ca), ptr(cd), ptr(scratch), ptr(out),
+                                   stream_ptr()), "svb_eer_sweep")
+    return out, ca, cd
+
+
 def eer_finish(cnt_all, cnt_diag, Mv):
     N, T = (int(s) for s in cnt_all.shape)
     out = torch.empty(4 + 2 * T, dtype=torch.float32, device=cnt_all.device)
