@@ -32,6 +32,11 @@ const char* svb_last_error(void);
 int svb_gemm_bf16(const void* const* A, const void* const* B, int nterms, float* C, const float* bias, int M, int N,
                   int K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn, int b_mn, void* stream);
 
+/* Same contract computed by CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 pair tiles); mn = 0: both operands
+ * K-major, mn = 1: both MN-major. */
+int svb_gemm_bf16_2cta(const void* const* A, const void* const* B, int nterms, float* C, const float* bias, int M,
+                       int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int mn, void* stream);
+
 /* ---- SpeechEmbedder (speech_embedder_net.py:15-33): 3-layer LSTM + last-frame Linear + L2 norm ------------------
  * Dimensions: B utterances, T frames, I mel bins, H hidden (multiple of 128), L layers (<= 8), P projection size. */
 

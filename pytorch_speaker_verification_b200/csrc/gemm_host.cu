@@ -83,3 +83,37 @@ extern "C" int svb_gemm_bf16(const void* const* A, const void* const* B, int nte
   else err = launch_tc_gemm<128, 4, true, false, EpiStoreF32<128>>(ops, ep, s);
   return err == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
 }
+
+// CTA-pair variant (tcgen05.mma.cta_group::2, 256 x 256 pair tiles): both operands K-major (mn = 0) or both
+// MN-major (mn = 1).
+extern "C" int svb_gemm_bf16_2cta(const void* const* A, const void* const* B, int nterms, float* C, const float* bias,
+                                  int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int mn, void* stream) {
+  if (nterms < 1 || nterms > kMaxTerms) return SVB_ERR_ARG;
+  GemmOperands ops;
+  memset(&ops, 0, sizeof(ops));
+  ops.nterms = nterms; ops.M = M; ops.N = N; ops.K = K;
+  for (int t = 0; t < nterms; ++t) {
+    int e = make_operand_map(&ops.ta[t], A[t], M, K, lda, mn, kBM);
+    if (e) return e;
+    e = make_operand_map(&ops.tb[t], B[t], N, K, ldb, mn, 128);     // each CTA of the pair loads 128 of the 256 B rows
+    if (e) return e;
+  }
+  if (mn) {
+    EpiStoreF32<256>::Params ep;
+    int e = make_store_params<256>(&ep, C, bias, M, N, ldc, 0);
+    if (e) return e;
+    cudaError_t err = launch_tc_gemm<256, 6, true, true, EpiStoreF32<256>, 8, 1, true>(
+        ops, ep, reinterpret_cast<cudaStream_t>(stream));
+    if (err != cudaSuccess) fprintf(stderr, "svb_gemm_bf16_2cta: %s\n", cudaGetErrorString(err));
+    return err == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+  }
+  EpiStoreF32<256>::Params ep;
+  {
+    int e = make_store_params<256>(&ep, C, bias, M, N, ldc, 0);
+    if (e) return e;
+  }
+  cudaError_t err = launch_tc_gemm<256, 6, false, false, EpiStoreF32<256>, 8, 1, true>(
+      ops, ep, reinterpret_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) fprintf(stderr, "svb_gemm_bf16_2cta: %s\n", cudaGetErrorString(err));
+  return err == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}

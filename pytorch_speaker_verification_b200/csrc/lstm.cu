@@ -32,6 +32,7 @@ struct LayerW {
   __nv_bfloat16 *wih_hi, *wih_lo;   // [4H, Ip] packed rows
   __nv_bfloat16 *whh_hi, *whh_lo;   // [4H, H]  packed rows
   __nv_bfloat16 *whhT;              // [H, 4H]  transpose of whh_hi (B operand of the BPTT frame GEMM)
+  __nv_bfloat16 *wihT;              // [Ip, 4H] transpose of wih_hi (B operand of dX = dG W_ih)
   float* bias;                      // [4H] packed, b_ih + b_hh
   int I, Ip;
 };
@@ -51,6 +52,7 @@ static PackedW layout_packed(char* base, int I, int H, int L) {
     pw.l[l].whh_hi = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
     pw.l[l].whh_lo = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
     pw.l[l].whhT = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
+    pw.l[l].wihT = (__nv_bfloat16*)take((size_t)4 * H * Ip * 2);
     pw.l[l].bias = (float*)take((size_t)4 * H * 4);
   }
   pw.bytes = off;
@@ -67,6 +69,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     lw.wih_hi[(size_t)p * lw.Ip + k] = hi;
     lw.wih_lo[(size_t)p * lw.Ip + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    lw.wihT[(size_t)k * 4 * H + p] = hi;
   }
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     const float v = w_hh[(size_t)r * H + k];
@@ -636,12 +639,13 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       const void* Bs[3] = {lw.wih_hi, lw.wih_hi, lw.wih_lo};
       for (int t = 0; t < 3; ++t) {
         SVB_TRY(make_operand_map(&ops.ta[t], As[t], T * B, lw.Ip, lw.Ip, 0, kBM));
-        SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 256));
+        SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 128));
       }
-      // 128 x 256 tiles: a 128 x 128 tile needs 128 B/clk of operands, twice what one SM can pull from L2
+      // CTA pairs, 256 x 256 pair tiles (tcgen05.mma.cta_group::2): a single-CTA 128 x 256 tile needs 96 B/clk of
+      // operands, a pair tile 64 B/clk -- which is what one SM can pull from L2
       EpiStoreF32<256>::Params ep;
       SVB_TRY(make_store_params<256>(&ep, w.gin, lw.bias, T * B, 4 * H, (int64_t)4 * H, 0));
-      cudaError_t e = launch_tc_gemm<256, 4, false, false, EpiStoreF32<256>, 8>(ops, ep, s);
+      cudaError_t e = launch_tc_gemm<256, 6, false, false, EpiStoreF32<256>, 8, 1, true>(ops, ep, s);
       if (e != cudaSuccess) { set_error("input projection", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_REC_FWD, s);
@@ -768,10 +772,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], 4 * H, TB, 4 * H, 1, 0));
       SVB_TRY(make_operand_map(&g.tb[0], w.h_hi[l], H, TB, H, 1, 0));           // h_{t-1}: slots 0..T-1
       cudaError_t e;
-      if (false && H % 256 == 0) {
-        EpiStoreF32<256>::Params ep;
-        SVB_TRY(make_store_params<256>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
-        e = launch_tc_gemm<256, 4, true, true, EpiStoreF32<256>>(g, ep, s);
+      if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
+        EpiStoreF32<128>::Params ep;
+        SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
+        e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep, s);
       } else {
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
@@ -780,10 +784,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
       SVB_TRY(make_operand_map(&g.tb[0], xin, lw.Ip, TB, lw.Ip, 1, 0));
-      if (false && lw.I % 256 == 0) {
-        EpiStoreF32<256>::Params ep2;
-        SVB_TRY(make_store_params<256>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
-        e = launch_tc_gemm<256, 4, true, true, EpiStoreF32<256>>(g, ep2, s);
+      if (lw.I % 128 == 0) {
+        EpiStoreF32<128>::Params ep2;
+        SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep2, s);
       } else {
         EpiStoreF32<128>::Params ep2;
         SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
@@ -806,13 +810,14 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       memset(&g, 0, sizeof(g));
       g.nterms = 1; g.M = TB; g.N = H; g.K = 4 * H;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], TB, 4 * H, 4 * H, 0, kBM));
-      SVB_TRY(make_operand_map(&g.tb[0], lw.wih_hi, H, 4 * H, lw.Ip, 1, 0));
       cudaError_t e;
-      if (H % 256 == 0) {
+      if (H % 256 == 0) {        // CTA pairs; B = W_ih^T [H rows, 4H] K-major
+        SVB_TRY(make_operand_map(&g.tb[0], lw.wihT, H, 4 * H, 4 * H, 0, 128));
         EpiStoreF32<256>::Params ep;
         SVB_TRY(make_store_params<256>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
-        e = launch_tc_gemm<256, 4, false, true, EpiStoreF32<256>, 8>(g, ep, s);
+        e = launch_tc_gemm<256, 6, false, false, EpiStoreF32<256>, 8, 1, true>(g, ep, s);
       } else {
+        SVB_TRY(make_operand_map(&g.tb[0], lw.wih_hi, H, 4 * H, lw.Ip, 1, 0));
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
         e = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>, 8>(g, ep, s);

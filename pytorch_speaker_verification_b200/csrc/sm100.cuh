@@ -120,6 +120,45 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// TMA load executed by either CTA of a pair into its OWN shared memory; the transaction bytes are credited to the
+// mbarrier of CTA 0 (the MMA leader): bit 24 of a shared::cluster address selects the CTA of the pair.
+__device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_holder) {   // same warp index in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), B rows split between the two CTAs' smem.
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once) on the mbarrier at the same offset in BOTH CTAs when the leader's prior MMAs have completed.
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------- TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder) {   // one full warp

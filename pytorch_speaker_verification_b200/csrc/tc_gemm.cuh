@@ -38,10 +38,10 @@ struct __align__(64) GemmOperands {
 // 1024-byte aligned): the unit index is XORed with (row mod 8).
 __device__ __forceinline__ uint32_t sw128(int row, int u16) { return row * 128 + ((u16 ^ (row & 7)) << 4); }
 
-template <int BN, int kStages, class Epi, int KSPLIT = 1>
+template <int BN, int kStages, class Epi, int KSPLIT = 1, bool TWO_CTA = false>
 struct GemmSmem {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (TWO_CTA ? BN / 2 : BN) * kBK * 2;   // a CTA pair splits the B rows
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static_assert(kStageBytes % 1024 == 0, "stages must keep 1024-byte alignment");
@@ -73,10 +73,14 @@ __device__ __forceinline__ void trace_stamp(const GemmOperands& ops, int slot) {
 // cluster each reduce a 1/KSPLIT slice of K for the same 128 x BN tile, exchange their partial 32-column chunks
 // through distributed shared memory, and CTA r finishes columns [32r, 32r+32) with Epi.  Each SM then pulls only
 // 1/KSPLIT of both operands from L2 -- the per-SM L2->SM port (~64 B/clk) is what bounds the BPTT frame.
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1>
+// TWO_CTA (cluster (2,1,1): blockIdx.x = 2*n_tile + rank, K-major operands): the two CTAs of a pair own adjacent 128-row tiles and each holds half
+// of the B rows; CTA 0 issues tcgen05.mma.cta_group::2 with M = 256, so every B byte is pulled from L2 once per 256
+// rows and the operand traffic per SM halves relative to the arithmetic.
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1, bool TWO_CTA = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __grid_constant__ GemmOperands ops,
                                                                const __grid_constant__ typename Epi::Params ep) {
-  using S = GemmSmem<BN, kStages, Epi, KSPLIT>;
+  using S = GemmSmem<BN, kStages, Epi, KSPLIT, TWO_CTA>;
+  static_assert(!TWO_CTA || KSPLIT == 1, "pair mode: no split-K");
   static_assert(KSPLIT == 1 || (BN == 32 * KSPLIT), "split-K layout");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,8 +93,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int kq = KSPLIT > 1 ? (int)cluster_ctarank() : 0;       // K slice (and finished column chunk) of this CTA
-  const int n0 = (blockIdx.x / KSPLIT) * BN;
-  const int m0 = blockIdx.y * kBM;
+  const int pair_rank = TWO_CTA ? (int)cluster_ctarank() : 0;   // 0 = MMA leader
+  const int n0 = (blockIdx.x / (TWO_CTA ? 2 : KSPLIT)) * BN;
+  const int m0 = TWO_CTA ? (blockIdx.y * 2 + (blockIdx.x & 1)) * kBM : blockIdx.y * kBM;
   const int nkb = ((ops.K + kBK - 1) / kBK) / KSPLIT;            // host guarantees divisibility
   const int kbase = kq * nkb * kBK;
   const int iters = nkb * ops.nterms;
@@ -114,10 +119,14 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     mbar_init(in_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_holder);
+  if (warp == 1) {
+    if (TWO_CTA) tmem_alloc_2cta<(BN < 32 ? 32 : BN)>(tmem_holder);
+    else tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_holder);
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");      // previous kernel complete and its writes visible
   tc_fence_before();
-  __syncthreads();
+  if (TWO_CTA) cluster_sync_all();                         // both CTAs' barriers initialised before remote arrives
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_holder;
 
@@ -137,6 +146,25 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
+        if constexpr (TWO_CTA) {
+          // both CTAs load their own A rows and their half of the B rows; all bytes are credited to the leader
+          if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+          if (A_MN) {
+            for (int j = 0; j < kBM / 64; ++j)
+              tma_load_3d_2cta(sa + j * (kBK * 128), &ops.ta[term], &full_bar[stage], m0 + 64 * j, k0, ops.za[term]);
+          } else {
+            tma_load_3d_2cta(sa, &ops.ta[term], &full_bar[stage], k0, m0, ops.za[term]);
+          }
+          if (B_MN) {
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_3d_2cta(sb + j * (kBK * 128), &ops.tb[term], &full_bar[stage],
+                               n0 + pair_rank * (BN / 2) + 64 * j, k0, ops.zb[term]);
+          } else {
+            tma_load_3d_2cta(sb, &ops.tb[term], &full_bar[stage], k0, n0 + pair_rank * (BN / 2), ops.zb[term]);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_expect_tx(&full_bar[stage], S::kStageBytes);
         if (A_MN) {
           for (int j = 0; j < kBM / 64; ++j)
@@ -156,10 +184,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(TWO_CTA ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < (TWO_CTA && pair_rank != 0 ? 0 : iters); ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
@@ -174,10 +202,16 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
                                    : umma_desc_kmajor_sw128(sa + k * 32);
           const uint64_t db = B_MN ? umma_desc_mnmajor_sw128(sb + k * 2048, kBK * 128)
                                    : umma_desc_kmajor_sw128(sb + k * 32);
-          umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          if (TWO_CTA) umma_bf16_ss_2cta(tmem_d, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          else umma_bf16_ss(tmem_d, da, db, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
-        if (it == iters - 1) umma_commit(accum_bar);  // accumulator complete, operand ring idle
+        if (TWO_CTA) {
+          umma_commit_2cta(&empty_bar[stage]);              // frees the slot in both CTAs
+          if (it == iters - 1) umma_commit_2cta(accum_bar);
+        } else {
+          umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+          if (it == iters - 1) umma_commit(accum_bar);  // accumulator complete, operand ring idle
+        }
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -281,8 +315,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     cluster_sync_all();                                              // peers are done reading my partials
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
+  if (TWO_CTA) cluster_sync_all();                         // neither CTA leaves while its peer may still signal it
+  else __syncthreads();
+  if (warp == 1) {
+    if (TWO_CTA) tmem_dealloc_2cta<(BN < 32 ? 32 : BN)>(tmem_d);
+    else tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_d);
+  }
   if (threadIdx.x == 0) trace_stamp(ops, 10);
 }
 
@@ -300,10 +338,10 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, u
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                    uint64_t stride2_elems, uint32_t box_rows);
 
-template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1>
+template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 4, int KSPLIT = 1, bool TWO_CTA = false>
 cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t stream) {
-  using S = GemmSmem<BN, kStages, Epi, KSPLIT>;
-  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps, KSPLIT>;
+  using S = GemmSmem<BN, kStages, Epi, KSPLIT, TWO_CTA>;
+  auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps, KSPLIT, TWO_CTA>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -313,6 +351,10 @@ cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(((ops.N + BN - 1) / BN) * KSPLIT, (ops.M + kBM - 1) / kBM);
+  if (TWO_CTA) {       // x = 2 * n_tiles (pair rank in the low bit), y = pairs of 128-row tiles (odd tail: all OOB)
+    cfg.gridDim.x *= 2;
+    cfg.gridDim.y = (cfg.gridDim.y + 1) / 2;
+  }
   cfg.blockDim = dim3(64 + 32 * kEpiWarps);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
@@ -325,6 +367,13 @@ cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& 
     if (((ops.K + kBK - 1) / kBK) % KSPLIT != 0) return cudaErrorInvalidValue;
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = KSPLIT;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  if (TWO_CTA) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
