@@ -122,6 +122,105 @@ def cpu_reference_rate(steps, warmup, budget_s=150.0):
     return n * M_UTT / dt, sample, cores, dt
 
 
+def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
+    """The other rows of SURVEY section 8: d-vector extraction (configs[3] shape, scaled down to a bounded shard per
+    GPU), the EER sweep at configs[4] size and the fused GE2E kernel alone; device time via CUDA events."""
+    import ctypes
+    import numpy as np
+    from pytorch_speaker_verification_b200 import eer as E, ops
+    from pytorch_speaker_verification_b200._lib import ptr, stream_ptr
+    L = _lib.lib()
+    out = {}
+
+    def dev_time(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # ---- d-vector extraction: 2000 utterances per GPU, T_u ~ U[100, 500] frames, from host log-mel arrays
+    r = np.random.RandomState(4321 + rank)
+    Ts = r.randint(100, 501, size=2000)
+    specs = [np.log10(I.power_spec(int(T), seed=int(T) + 7 * i) + 1e-6).astype(np.float32) for i, T in enumerate(Ts[:64])]
+    specs = [specs[i % 64][:, :int(T)] if specs[i % 64].shape[1] >= T else np.tile(specs[i % 64], (1, 8))[:, :int(T)]
+             for i, T in enumerate(Ts)]
+    was_training = net.training
+    net.eval()
+    outs = svb.extract_dvectors(net, specs)                     # warm-up (also allocates)
+    t0 = time.perf_counter()
+    outs = svb.extract_dvectors(net, specs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nwin = int(sum(max(0, -(-(int(T) - 24) // 12)) for T in Ts))
+    ndv = int(sum(len(o) for o in outs))
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["extraction"] = {"utterances_per_gpu": len(specs), "windows_per_gpu": nwin, "dvectors_per_gpu": ndv,
+                         "seconds": t.item(), "windows_per_s": world * nwin / t.item(),
+                         "dvectors_per_s": world * ndv / t.item(), "utterances_per_s": world * len(specs) / t.item(),
+                         "path": "host log-mel -> H2D -> window gather -> LSTM fwd (T=24) -> partition mean -> D2H"}
+    # device-resident part only: LSTM forward of 32768 windows x 24 frames already in HBM (the tensor-bound core)
+    xw = torch.tensor(I.logmel(4096, 24, seed=99)).to(dev).repeat(8, 1, 1)
+    with torch.no_grad():
+        ms = dev_time(lambda: net(xw), 3, 1)
+    out["extraction"]["lstm_forward_windows_per_s_device_resident"] = world * xw.shape[0] / (ms * 1e-3)
+    out["extraction"]["lstm_forward_frac_of_tensor_roofline"] = (xw.shape[0] / (ms * 1e-3)) * 572522496.0 / 1e12 / \
+        peaks()[0].get("bf16_tflops_sustained", 1400.0)
+    net.train(was_training)
+    if rank != 0:
+        return out
+
+    # ---- EER sweep at N=1024, M=6 (3 enrollment + 3 verification)
+    enr, ver = I.eer_embeddings(1024, 6, 0.06, 0.5, 4242)
+    enr, ver = torch.tensor(enr).to(dev), torch.tensor(ver).to(dev)
+    with torch.no_grad():
+        sim = svb.get_cossim(ver, svb.get_centroids(enr)).contiguous()
+    thr = E._thresholds_f32(sim.device, E.THRESHOLDS)
+    N, Mv, T = 1024, 3, 50
+    ca = torch.empty(N, T, dtype=torch.int32, device=dev)
+    cd = torch.empty_like(ca)
+    scratch = torch.zeros(1 + 16 * T, dtype=torch.int64, device=dev)
+    res = torch.empty(4 + 2 * T, device=dev)
+    st = stream_ptr()
+
+    def sweep():
+        scratch.zero_()
+        L.svb_eer_sweep(ptr(sim), N, Mv, ptr(thr), T, ptr(ca), ptr(cd), ptr(scratch), ptr(res), st)
+
+    ms = dev_time(sweep, 100, 10)
+    with torch.no_grad():
+        ms_cos = dev_time(lambda: svb.get_cossim(ver, svb.get_centroids(enr)), 20, 3)
+    out["eer"] = {"N": N, "M": 6, "sweep_us": ms * 1e3, "sim_bytes": sim.numel() * 4,
+                  "sweep_GBps": sim.numel() * 4 / (ms * 1e-3) / 1e9, "cossim_from_embeddings_us": ms_cos * 1e3,
+                  "eer": float(res[0])}
+
+    # ---- fused GE2E forward+backward alone (raw C ABI, preallocated buffers)
+    for (Ns, Ms) in ((64, 10), (512, 10)):
+        Eg = torch.tensor(I.ge2e_embeddings(Ns, Ms, 256, "unit")).to(dev)
+        w = torch.tensor(10.0, device=dev)
+        b = torch.tensor(-5.0, device=dev)
+        nb = ctypes.c_size_t(0)
+        L.svb_ge2e_workspace_bytes(Ns, Ms, 256, Ns, ctypes.byref(nb))
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), device=dev)
+        dE = torch.empty_like(Eg)
+        dw = torch.empty((), device=dev)
+        db = torch.empty((), device=dev)
+        ms = dev_time(lambda: L.svb_ge2e(ptr(Eg), None, Ns, Ms, 256, Ns, ptr(w), ptr(b), None, None, None, None,
+                                         ptr(loss), ptr(dE), None, ptr(dw), ptr(db), ptr(ws),
+                                         ctypes.c_size_t(nb.value), 1, st), 100, 10)
+        out[f"ge2e_fwd_bwd_N{Ns}"] = {"us": ms * 1e3, "algorithmic_bytes": 2 * Eg.numel() * 4,
+                                      "GBps": 2 * Eg.numel() * 4 / (ms * 1e-3) / 1e9}
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -251,6 +350,7 @@ def main():
     phases = phase_profile(value_step)          # every rank: the step contains collectives
     barrier()
     loss_val = float(loss_host)
+    extra = secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world)
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -295,6 +395,7 @@ def main():
                          # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)
                          "whole_step_frac": 11443765248.0 * B / 1e12 / (ms_value * 1e-3) / peak},
             "phases_ms": phases,
+            "secondary": extra,
             "loss": loss_val,
         }
         if world == 1 and not args.no_cpu_baseline:

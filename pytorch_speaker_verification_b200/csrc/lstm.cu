@@ -528,6 +528,7 @@ struct Profiler {
 };
 static Profiler g_prof;
 static int g_persistent = 0;
+static int g_fwd_pair = 0;     // forward frame: CTA pairs share the W_hh slice (measured slower: cluster barriers outweigh the ingest saving)
 static int g_bwd_splitk = 1;   // BPTT frame: 4-CTA cluster split-K with DSMEM partial exchange
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
 static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
@@ -548,9 +549,9 @@ static int check_dims(const Dims& d) {
   return SVB_OK;
 }
 
-template <class Epi, int BN, int kStages, bool B_MN, int kEpiWarps, int KSPLIT = 1>
+template <class Epi, int BN, int kStages, bool B_MN, int kEpiWarps, int KSPLIT = 1, bool TWO_CTA = false>
 static int launch_step(GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t s) {
-  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi, kEpiWarps, KSPLIT>(ops, ep, s);
+  cudaError_t e = launch_tc_gemm<BN, kStages, false, B_MN, Epi, kEpiWarps, KSPLIT, TWO_CTA>(ops, ep, s);
   if (e != cudaSuccess) { set_error("lstm step launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }
@@ -560,6 +561,7 @@ using namespace svb;
 
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
+extern "C" int svb_set_fwd_pair(int on) { g_fwd_pair = on != 0; return SVB_OK; }
 extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
 extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
 extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
@@ -681,8 +683,12 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     memset(&ops, 0, sizeof(ops));
     // terms: h_hi W_hi (+ h_hi W_lo (+ h_lo W_hi)): rec_terms > 1 buys accuracy for large-magnitude weights
     ops.nterms = rec_terms; ops.M = B; ops.N = 4 * H; ops.K = H;
+    // rec_terms == 1: CTA pairs (two 128-row batch tiles share each W_hh slice, 64 rows per CTA)
+    // (pays off once the batch spans several waves of CTAs: extraction batches; at B = 640 the two cluster barriers
+    //  per frame cost more than the halved W_hh traffic saves)
+    const bool fwd_pair = (rec_terms == 1) && (g_fwd_pair || B > 1024);
     SVB_TRY(make_tmap_bf16(&ops.ta[0], w.h_hi[l], H, B, T + 1, H, BH, kBM));
-    SVB_TRY(make_operand_map(&ops.tb[0], lw.whh_hi, 4 * H, H, H, 0, 128));
+    SVB_TRY(make_operand_map(&ops.tb[0], lw.whh_hi, 4 * H, H, H, 0, fwd_pair ? 64 : 128));
     ops.ta[1] = ops.ta[0];
     SVB_TRY(make_operand_map(&ops.tb[1], lw.whh_lo, 4 * H, H, H, 0, 128));
     SVB_TRY(make_tmap_bf16(&ops.ta[2], w.h_lo[l], H, B, T + 1, H, BH, kBM));
@@ -705,7 +711,8 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       ep.c_prev_slot = training ? t : (t & 1);
       ep.c_out_slot = training ? t + 1 : ((t + 1) & 1);
       ep.h_f32 = (l == L - 1 && t == T - 1) ? w.h_last : nullptr;
-      SVB_TRY((launch_step<EpiLstmFwd, 128, 4, false, 8>(ops, ep, s)));
+      if (fwd_pair) SVB_TRY((launch_step<EpiLstmFwd, 128, 5, false, 8, 1, true>(ops, ep, s)));
+      else SVB_TRY((launch_step<EpiLstmFwd, 128, 4, false, 8>(ops, ep, s)));
     }
   }
   prof_mark(PH_PROJ, s);

@@ -55,6 +55,17 @@ def align_embeddings(embeddings):
     return out.cpu().numpy()
 
 
+_part_cache = {}
+
+
+def _cached_partition_offsets(W):
+    po = _part_cache.get(W)
+    if po is None:
+        po = partition_offsets(W)
+        _part_cache[W] = po
+    return po
+
+
 @torch.no_grad()
 def extract_dvectors(embedder_net, specs, max_windows=65536):
     """Batched extraction for many utterances: specs = list of (nmels, T_u) log-mel arrays.
@@ -62,28 +73,30 @@ def extract_dvectors(embedder_net, specs, max_windows=65536):
     launch and one segment-mean launch for the whole batch; the LSTM runs on chunks of <= max_windows windows."""
     dev = ops._dev()
     with torch.cuda.device(dev):
-        Ts = [int(s.shape[1]) for s in specs]
-        nm = int(specs[0].shape[0])
+        Ts = np.asarray([int(s.shape[1]) for s in specs], dtype=np.int64)
         cat = torch.from_numpy(np.concatenate([np.asarray(s, dtype=np.float32) for s in specs], axis=1))
         cat = cat.pin_memory().to(dev, non_blocking=True)
-        starts, seg, counts = [], [0], []
-        base = 0
-        for T in Ts:
-            ws = window_starts(T)
-            starts.append(ws + base)
-            po = partition_offsets(len(ws))
-            if len(ws):
-                seg.extend((po[1:] + len(np.concatenate(starts)) - len(ws)).tolist())
-            counts.append(len(po) - 1 if len(ws) else 0)
-            base += T
-        starts = np.concatenate(starts).astype(np.int32)
-        W = len(starts)
+        nw = np.where(Ts > WIN, -(-(Ts - WIN) // HOP), 0)                 # windows per utterance (strict j+24 < T)
+        base = np.concatenate([[0], np.cumsum(Ts)[:-1]])                  # first frame of each utterance
+        W = int(nw.sum())
         D = embedder_net.projection.out_features
         if W == 0:
             return [np.zeros((0, D)) for _ in specs]
+        wfirst = np.concatenate([[0], np.cumsum(nw)[:-1]])               # first window index of each utterance
+        within = np.arange(W, dtype=np.int64) - np.repeat(wfirst, nw)
+        starts = (np.repeat(base, nw) + HOP * within).astype(np.int32)
+        seg, counts = [np.zeros(1, dtype=np.int64)], []
+        for n, w0 in zip(nw.tolist(), wfirst.tolist()):
+            if n:
+                po = _cached_partition_offsets(n)
+                seg.append(po[1:].astype(np.int64) + w0)
+                counts.append(len(po) - 1)
+            else:
+                counts.append(0)
+        seg = np.concatenate(seg).astype(np.int32)
         frames = ops.dvector_windows(cat, torch.from_numpy(starts).to(dev), WIN)
         emb = torch.cat([embedder_net(frames[i:i + max_windows]) for i in range(0, W, max_windows)], dim=0)
-        out = ops.segment_mean(emb, torch.tensor(seg, dtype=torch.int32, device=dev)).cpu().numpy()
+        out = ops.segment_mean(emb, torch.from_numpy(seg).to(dev)).cpu().numpy()
     res, o = [], 0
     for c in counts:
         res.append(out[o:o + c])
