@@ -190,8 +190,7 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
     res = torch.empty(4 + 2 * T, device=dev)
     st = stream_ptr()
 
-    def sweep():
-        scratch.zero_()
+    def sweep():                      # scratch is re-zeroed by the kernel's last block
         L.svb_eer_sweep(ptr(sim), N, Mv, ptr(thr), T, ptr(ca), ptr(cd), ptr(scratch), ptr(res), st)
 
     ms = dev_time(sweep, 100, 10)
@@ -390,7 +389,12 @@ def main():
             "gpu_launches": launches_per_step(world) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": f"{pk_src} (sustained bf16)",
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                         # (profiles/r1_ncu_full_summary.txt); the frame kernels' writes stay in the 126 MB L2
+                         "traffic": {"recurrent_fwd": 15556352, "recurrent_bwd": 18506752,
+                                     "input_gemm": 325408256 + 1203885000}.get(dom),
+                         "peak_source": f"{pk_src} (sustained bf16)",
                          "avg_launch_us": avg_ms * 1e3, "launches_per_step": launches,
                          # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)
                          "whole_step_frac": 11443765248.0 * B / 1e12 / (ms_value * 1e-3) / peak},

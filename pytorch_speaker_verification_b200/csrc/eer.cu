@@ -145,85 +145,83 @@ __device__ __forceinline__ void eer_scan(const float* far_s, const float* frr_s,
 
 constexpr int kSweepWarps = 4;
 constexpr int kBk = 64;           // bucket rows of the lane-private histogram (T + 1 <= 64 on this path)
-// scratch (zeroed by the host): [0] block ticket, then 8 replicas of the totals [8][2][T]: sum over speakers of
+// scratch (zeroed once by the host; the last block re-zeroes it): [0] block ticket, then 8 replicas of the totals [8][2][T]: sum over speakers of
 // (cnt_all - cnt_diag) and of cnt_diag, accumulated with integer atomics (exact in any order).
+// One CTA (4 warps) per speaker: each warp takes a quarter of the speaker's (Mv x N) row block.
 __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float* __restrict__ sim, int N, int Mv, int Nc,
                                                                      const float* __restrict__ thr_g, int T,
                                                                      int* __restrict__ cnt_all, int* __restrict__ cnt_diag,
                                                                      unsigned long long* __restrict__ scratch,
                                                                      float* __restrict__ out) {
   __shared__ float thr[kBk];
-  __shared__ int hist[kSweepWarps][kBk][32];      // lane-private columns: plain increments, no bank conflicts
-  __shared__ int hsum[kSweepWarps][2][kBk];
+  // lane-private columns (uncontended increments, no bank conflicts); two 16-bit buckets per word so that a CTA
+  // needs 16 KB and all N CTAs are resident in one wave (a lane sees < 65536 elements: checked by the host)
+  __shared__ int hist[kSweepWarps][kBk / 2][32];
+  __shared__ int wsum[kSweepWarps][kBk];
+  __shared__ int h_diag[kBk];
   __shared__ float far_s[kMaxThr], frr_s[kMaxThr];
-  __shared__ int btot[2][kMaxThr];
   __shared__ int last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = threadIdx.x; t < kBk; t += blockDim.x) {
     thr[t] = t < T ? thr_g[t] : INFINITY;
-    btot[0][t] = 0; btot[1][t] = 0;
+    h_diag[t] = 0;
   }
-  for (int bk = 0; bk <= T; ++bk) hist[warp][bk][lane] = 0;
-  for (int t = lane; t < kBk; t += 32) { hsum[warp][0][t] = 0; hsum[warp][1][t] = 0; }
+  for (int bk = 0; bk < kBk / 2; ++bk) hist[warp][bk][lane] = 0;
   __syncthreads();
-  const int i = blockIdx.x * kSweepWarps + warp;
-  if (i < N) {
-    const float* base = sim + (size_t)i * Mv * Nc;
-    const float t0 = thr[0];
-    const int n = Mv * Nc;
-    int (*h)[32] = hist[warp];
-    int* h_all = hsum[warp][0];
-    int* h_diag = hsum[warp][1];
-    if ((Nc & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
-      const float4* b4 = reinterpret_cast<const float4*>(base);
-      const int n4 = n >> 2;
-      for (int q0 = 0; q0 < n4; q0 += 32 * 8) {
-        float4 v[8];
+  const int i = blockIdx.x;
+  const float* base = sim + (size_t)i * Mv * Nc;
+  const float t0 = thr[0];
+  const int n = Mv * Nc;
+  int (*h)[32] = hist[warp];
+  if ((Nc & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    const int n4 = n >> 2;
+    for (int q0 = 0; q0 < n4; q0 += 128 * 8) {
+      float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int q = q0 + u * 32 + lane;
-          v[u] = q < n4 ? __ldg(b4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u * 128 + threadIdx.x;
+        v[u] = q < n4 ? __ldg(b4 + q) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      for (int u = 0; u < 8; ++u) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) atomicAdd(&h[bucket_of64(vv[e], thr)][lane], 1);   // lane-private: no contention
+        for (int e = 0; e < 4; ++e) {
+          const int bk = bucket_of64(vv[e], thr);
+          atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
         }
       }
-    } else {
-      for (int idx = lane; idx < n; idx += 32) {
-        const float v = base[idx];
-        atomicAdd(&h[bucket_of64(v, thr)][lane], 1);
-      }
     }
-    for (int m = lane; m < Mv; m += 32) {               // the diagonal column of this speaker's row block
-      const float v = base[(size_t)m * Nc + i];
-      if (v > t0) atomicAdd(&h_diag[bucket_of64(v, thr)], 1);
+  } else {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+      const int bk = bucket_of64(base[idx], thr);
+      atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
     }
-    __syncwarp();
-    for (int bk = lane; bk <= T; bk += 32) {            // fold the 32 lane-private columns of each bucket
-      int tot = 0;
+  }
+  for (int m = threadIdx.x; m < Mv; m += blockDim.x) {      // the diagonal column of this speaker's row block
+    const float v = base[(size_t)m * Nc + i];
+    if (v > t0) atomicAdd(&h_diag[bucket_of64(v, thr)], 1);
+  }
+  __syncwarp();
+  for (int bk = lane; bk <= T; bk += 32) {                  // fold the 32 lane-private columns of each bucket
+    int tot = 0;
 #pragma unroll 8
-      for (int l = 0; l < 32; ++l) tot += h[bk][(l + lane) & 31];
-      h_all[bk] = tot;
-    }
-    __syncwarp();
-    for (int t = lane; t < T; t += 32) {                // count(sim > thr[t]) = sum_{bk > t} hist[bk]
-      int sa = 0, sd = 0;
-      for (int bk = t + 1; bk <= T; ++bk) { sa += h_all[bk]; sd += h_diag[bk]; }
-      cnt_all[(size_t)i * T + t] = sa;
-      cnt_diag[(size_t)i * T + t] = sd;
-      if (sa - sd) atomicAdd(&btot[0][t], sa - sd);
-      if (sd) atomicAdd(&btot[1][t], sd);
-    }
+    for (int l = 0; l < 32; ++l) tot += (h[bk >> 1][(l + lane) & 31] >> ((bk & 1) * 16)) & 0xffff;
+    wsum[warp][bk] = tot;
   }
   __syncthreads();
-  // integer atomics (exact, order-independent) into one of 8 replicas of the totals to spread same-address traffic
-  unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x & 7) * 2 * T;
-  for (int t = threadIdx.x; t < 2 * T; t += blockDim.x) {
-    const int v = btot[t / T][t % T];
-    if (v) atomicAdd(&part[t], (unsigned long long)v);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {       // count(sim > thr[t]) = sum_{bk > t} hist[bk]
+    int sa = 0, sd = 0;
+    for (int bk = t + 1; bk <= T; ++bk) {
+      sa += wsum[0][bk] + wsum[1][bk] + wsum[2][bk] + wsum[3][bk];
+      sd += h_diag[bk];
+    }
+    cnt_all[(size_t)i * T + t] = sa;
+    cnt_diag[(size_t)i * T + t] = sd;
+    unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x & 7) * 2 * T;
+    if (sa - sd) atomicAdd(&part[t], (unsigned long long)(sa - sd));
+    if (sd) atomicAdd(&part[T + t], (unsigned long long)sd);
   }
   __threadfence();
   __syncthreads();
@@ -249,6 +247,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
     out[4 + t] = FAR; out[4 + T + t] = FRR;
   }
   const int all_exact = __syncthreads_and(exact ? 1 : 0);
+  for (int t = threadIdx.x; t < 1 + 16 * T; t += blockDim.x) scratch[t] = 0;   // self-cleaning: ready for the next call
   if (threadIdx.x == 0) {
     eer_scan(far_s, frr_s, T, out);
     if (!all_exact) out[1] = -2.0f;                     // caller falls back to the sequential float32 kernel
@@ -284,11 +283,12 @@ extern "C" int svb_eer_finish(const int* cnt_all, const int* cnt_diag, int N, in
  * longer exact): call svb_eer_finish on the per-speaker counts instead. */
 extern "C" int svb_eer_sweep(const float* sim, int N, int Mv, const float* thresholds, int T, int* cnt_all,
                              int* cnt_diag, unsigned long long* scratch, float* out, void* stream) {
-  if (!sim || !thresholds || !cnt_all || !cnt_diag || !scratch || !out || N < 2 || Mv < 1 || T < 1 || T >= kBk) {
-    set_error("svb_eer_sweep: bad argument (T must be < 64)", cudaSuccess);
+  if (!sim || !thresholds || !cnt_all || !cnt_diag || !scratch || !out || N < 2 || Mv < 1 || T < 1 || T >= kBk ||
+      (long long)Mv * N >= 65536LL * 128) {
+    set_error("svb_eer_sweep: bad argument (T must be < 64, Mv*N < 2^23)", cudaSuccess);
     return SVB_ERR_ARG;
   }
-  eer_sweep_kernel<<<(N + kSweepWarps - 1) / kSweepWarps, 32 * kSweepWarps, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  eer_sweep_kernel<<<N, 32 * kSweepWarps, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       sim, N, Mv, N, thresholds, T, cnt_all, cnt_diag, scratch, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("svb_eer_sweep", e); return SVB_ERR_CUDA; }

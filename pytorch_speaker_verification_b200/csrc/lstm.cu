@@ -96,7 +96,7 @@ struct Work {
   int cslots;
   size_t bytes;
 };
-constexpr int kColsumRows = 2048;
+constexpr int kColsumRows = 256;
 static Work layout_work(char* base, const Dims& d, int training) {
   Work w{};
   size_t off = 0;
@@ -492,17 +492,22 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 // Column sums of dG [rows, 4H] (bf16, packed columns) -> partial sums per row chunk, then unpack + reduce.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
                                                           int64_t rows, int cols) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
+  // thread = 8 consecutive columns (one 16-byte load per row); blockIdx.y = chunk of kColsumRows rows
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (c >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * kColsumRows;
   const int64_t r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
-  float a0 = 0.f, a1 = 0.f;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll 8
   for (int64_t r = r0; r < r1; ++r) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(x + r * cols + c);
-    a0 += bf16_lo_of(v); a1 += bf16_hi_of(v);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * cols + c));
+    a[0] += bf16_lo_of(v.x); a[1] += bf16_hi_of(v.x); a[2] += bf16_lo_of(v.y); a[3] += bf16_hi_of(v.y);
+    a[4] += bf16_lo_of(v.z); a[5] += bf16_hi_of(v.z); a[6] += bf16_lo_of(v.w); a[7] += bf16_hi_of(v.w);
   }
-  part[(size_t)blockIdx.y * cols + c] = a0;
-  part[(size_t)blockIdx.y * cols + c + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[(size_t)blockIdx.y * cols + c + j] = a[j];
 }
 __global__ void bias_grad_finish_kernel(const float* __restrict__ part, int chunks, int H, float* __restrict__ g_ih,
                                         float* __restrict__ g_hh) {
@@ -805,7 +810,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     prof_mark(PH_BIAS, s);
     {
       const int chunks = (TB + kColsumRows - 1) / kColsumRows;
-      dim3 grid((4 * H / 2 + 255) / 256, chunks);
+      dim3 grid((4 * H / 8 + 255) / 256, chunks);
       colsum_bf16_kernel<<<grid, 256, 0, s>>>(w.gates[l], w.colsum_part, TB, 4 * H);
       bias_grad_finish_kernel<<<(4 * H + 255) / 256, 256, 0, s>>>(w.colsum_part, chunks, H, grads[4 * l + 2], grads[4 * l + 3]);
       SVB_CUDA("bias grads");

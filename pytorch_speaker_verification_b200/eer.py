@@ -27,7 +27,7 @@ def eer_sweep(sim_matrix, thresholds=None):
     with torch.cuda.device(ops._dev()):
         sim = ops._stage(sim_matrix.detach(), torch.float32)
         thr = _thresholds_f32(sim.device, thresholds)
-        if sim.shape[0] == sim.shape[2] and sim.shape[0] >= 2 and len(thresholds) < 64:
+        if sim.shape[0] == sim.shape[2] and sim.shape[0] >= 2 and len(thresholds) < 64 and sim.shape[1] * sim.shape[2] < (1 << 23):
             out_d, ca, cd = ops.eer_sweep_fused(sim, thr)
             out = out_d.cpu()
             if int(out[1]) == -2:                       # totals beyond 2^24: sequential float32 emulation

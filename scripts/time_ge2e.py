@@ -47,7 +47,6 @@ ca = torch.empty(N, T, dtype=torch.int32, device="cuda"); cd = torch.empty_like(
 scratch = torch.zeros(1 + 16 * T, dtype=torch.int64, device="cuda"); out = torch.empty(4 + 2 * T, device="cuda")
 st = stream_ptr()
 def sweep():
-    scratch.zero_()
     assert L.svb_eer_sweep(ptr(sim), N, Mv, ptr(thr), T, ptr(ca), ptr(cd), ptr(scratch), ptr(out), st) == 0
 us = timeit(sweep)
 print(f"EER fused sweep N=1024 Mv=3 (memset + 1 kernel): {us:.1f} us -> {sim.numel()*4/us/1e3:.0f} GB/s of {sim.numel()*4/1e6:.1f} MB")
