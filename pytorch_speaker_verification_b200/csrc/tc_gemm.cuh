@@ -68,7 +68,7 @@ __device__ __forceinline__ void trace_stamp(const GemmOperands& ops, int slot) {
 //   static __device__ void apply(const Params&, const uint8_t* in, uint8_t* out, int row, int m, int n0, int chunk,
 //                                float (&acc)[32], bool valid);                                   128 threads
 //   static __device__ void issue_stores(const Params&, const uint8_t* out, int m0, int n0);         one thread
-// kEpiWarps = 4 or 8 epilogue warps (8: two warps per TMEM lane quarter, each taking half of the column chunks).
+// kEpiWarps = 4, 8 or 16 epilogue warps (kEpiWarps/4 warps per TMEM lane quarter share the column chunks).
 // KSPLIT > 1 (requires BN == 32*KSPLIT, 4 epilogue warps, a (KSPLIT,1,1) cluster launch): the KSPLIT CTAs of a
 // cluster each reduce a 1/KSPLIT slice of K for the same 128 x BN tile, exchange their partial 32-column chunks
 // through distributed shared memory, and CTA r finishes columns [32r, 32r+32) with Epi.  Each SM then pulls only
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;            // 0 (or 1 with 8 epilogue warps)
     constexpr int kChunks = BN / 32;
-    constexpr int kPerWarp = (kEpiWarps == 8 && kChunks >= 2) ? kChunks / 2 : kChunks;
+    constexpr int kGroups = kEpiWarps / 4;                                   // warps per TMEM lane quarter
+    constexpr int kPerWarp = (kChunks >= kGroups) ? kChunks / kGroups : kChunks;
     const int row = q * 32 + lane_id();
     const int m = m0 + row;
     const bool valid = m < ops.M;
@@ -231,10 +232,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(ops, 6);
     if constexpr (KSPLIT == 1) {
-      if (kEpiWarps == 4 || kChunks >= 2 || half == 0) {
+      if (kChunks >= kGroups || half == 0) {
 #pragma unroll 1
         for (int cc = 0; cc < kPerWarp; ++cc) {
-          const int c = (kEpiWarps == 8 && kChunks >= 2) ? half * kPerWarp + cc : cc;
+          const int c = (kChunks >= kGroups) ? half * kPerWarp + cc : cc;
           float acc[32];
           tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + c * 32, acc);
           tmem_ld_wait();
