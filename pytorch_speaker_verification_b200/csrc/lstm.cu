@@ -4,17 +4,21 @@
 // and the BPTT that autograd runs for train_speech_embedder.py:62 in the reference.
 //
 // Data layout (all device memory, allocated by the caller):
-//   x_tm      [T, B, Ip]   bf16 hi / lo   time-major copy of the (B, T, I) input, Ip = I rounded up to 8
+//   x_tm      [T, B, Ip]   fp16 hi / lo (+ bf16 copy for the weight gradients)   time-major copy of the (B, T, I)
+//                                         input, Ip = I rounded up to 8
 //   gin       [T, B, 4H]   fp32           input projection W_ih x_t + b_ih + b_hh, PACKED gate columns
-//   hseq[l]   [T+1, B, H]  bf16 hi / lo   h_t in slot t+1, slot 0 = h_{-1} = 0
+//   hseq[l]   [T+1, B, H]  fp16 + bf16    h_t in slot t+1, slot 0 = h_{-1} = 0 (fp16: forward operand; bf16: operand
+//                                         of the weight-gradient GEMMs next to the bf16 dG)
 //   cseq[l]   [T+1, B, H]  fp32           c_t in slot t+1 (training; 2 slots otherwise)
 //   gates[l]  [T+1, B, 4H] bf16           sigma/tanh gate activations (training), overwritten in place by the
 //                                         gate pre-activation gradients dG during BPTT; slot T = 0
 // Packed gate order: column p = 32*(u/8) + 8*g + (u%8) for gate g in (i,f,g,o) of hidden unit u, so every
 // 32-column accumulator chunk that an epilogue thread owns holds all four gates of 8 units and the cell update
 // is fused into the recurrent GEMM's epilogue with no exchange between threads.
-// Numerics: recurrent GEMM bf16 x bf16 -> fp32; input projection split-bf16, 3 terms (x_hi W_hi + x_lo W_hi +
-// x_hi W_lo) accumulated in one TMEM accumulator; gates, cell state, projection and norm in fp32.
+// Numerics: forward GEMMs fp16 x fp16 -> fp32 (11-bit significands: 2e-4 embedding error with one term; the
+// layer-0 projection of the log-mel input keeps the 3-term hi/lo split, K = 40 makes it free); BPTT GEMMs bf16
+// (gradient range); gates, cell state, projection and norm in fp32.
+#include <cuda_fp16.h>
 #include "tc_gemm.cuh"
 #include "epilogues.cuh"
 #include "../../include/svb200.h"
@@ -29,10 +33,10 @@ static inline int round8(int x) { return (x + 7) & ~7; }
 
 // ------------------------------------------------------------------------------------------ packed weights
 struct LayerW {
-  __nv_bfloat16 *wih_hi, *wih_lo;   // [4H, Ip] packed rows
-  __nv_bfloat16 *whh_hi, *whh_lo;   // [4H, H]  packed rows
-  __nv_bfloat16 *whhT;              // [H, 4H]  transpose of whh_hi (B operand of the BPTT frame GEMM)
-  __nv_bfloat16 *wihT;              // [Ip, 4H] transpose of wih_hi (B operand of dX = dG W_ih)
+  __half *wih_hi, *wih_lo;          // [4H, Ip] packed rows, fp16 and fp16 residual
+  __half *whh_hi, *whh_lo;          // [4H, H]  packed rows
+  __nv_bfloat16 *whhT;              // [H, 4H]  bf16 transpose of W_hh (B operand of the BPTT frame GEMM)
+  __nv_bfloat16 *wihT;              // [Ip, 4H] bf16 transpose of W_ih (B operand of dX = dG W_ih)
   float* bias;                      // [4H] packed, b_ih + b_hh
   int I, Ip;
 };
@@ -47,10 +51,10 @@ static PackedW layout_packed(char* base, int I, int H, int L) {
   for (int l = 0; l < L; ++l) {
     const int Il = l == 0 ? I : H, Ip = round8(Il);
     pw.l[l].I = Il; pw.l[l].Ip = Ip;
-    pw.l[l].wih_hi = (__nv_bfloat16*)take((size_t)4 * H * Ip * 2);
-    pw.l[l].wih_lo = (__nv_bfloat16*)take((size_t)4 * H * Ip * 2);
-    pw.l[l].whh_hi = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
-    pw.l[l].whh_lo = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
+    pw.l[l].wih_hi = (__half*)take((size_t)4 * H * Ip * 2);
+    pw.l[l].wih_lo = (__half*)take((size_t)4 * H * Ip * 2);
+    pw.l[l].whh_hi = (__half*)take((size_t)4 * H * H * 2);
+    pw.l[l].whh_lo = (__half*)take((size_t)4 * H * H * 2);
     pw.l[l].whhT = (__nv_bfloat16*)take((size_t)4 * H * H * 2);
     pw.l[l].wihT = (__nv_bfloat16*)take((size_t)4 * H * Ip * 2);
     pw.l[l].bias = (float*)take((size_t)4 * H * 4);
@@ -66,17 +70,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
   const int r = g * H + u;                        // reference row (gate-major: i|f|g|o, speech_embedder_net.py:19)
   for (int k = threadIdx.x; k < lw.Ip; k += blockDim.x) {
     const float v = k < lw.I ? w_ih[(size_t)r * lw.I + k] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __half hi = __float2half_rn(v);
     lw.wih_hi[(size_t)p * lw.Ip + k] = hi;
-    lw.wih_lo[(size_t)p * lw.Ip + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    lw.wihT[(size_t)k * 4 * H + p] = hi;
+    lw.wih_lo[(size_t)p * lw.Ip + k] = __float2half_rn(v - __half2float(hi));
+    lw.wihT[(size_t)k * 4 * H + p] = __float2bfloat16_rn(v);
   }
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     const float v = w_hh[(size_t)r * H + k];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __half hi = __float2half_rn(v);
     lw.whh_hi[(size_t)p * H + k] = hi;
-    lw.whh_lo[(size_t)p * H + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    lw.whhT[(size_t)k * 4 * H + p] = hi;
+    lw.whh_lo[(size_t)p * H + k] = __float2half_rn(v - __half2float(hi));
+    lw.whhT[(size_t)k * 4 * H + p] = __float2bfloat16_rn(v);
   }
   if (threadIdx.x == 0) lw.bias[p] = b_ih[r] + b_hh[r];
 }
@@ -84,9 +88,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_ih, const float*
 // ------------------------------------------------------------------------------------------ workspace
 struct Dims { int B, T, I, H, L, P; };
 struct Work {
-  __nv_bfloat16 *x_hi, *x_lo;       // [T, B, Ip0]
+  __half *x_hi, *x_lo;              // [T, B, Ip0] fp16 and fp16 residual
+  __nv_bfloat16* x_bf;              // [T, B, Ip0] bf16 (training: operand of dW_ih of layer 0)
   float* gin;                       // [T, B, 4H]
-  __nv_bfloat16 *h_hi[8], *h_lo[8]; // [T+1, B, H]
+  __half* h_hi[8];                  // [T+1, B, H] fp16: forward operand
+  __nv_bfloat16* h_lo[8];           // [T+1, B, H] bf16 copy (training: operand of the weight-gradient GEMMs)
   float* c[8];                      // [cslots, B, H]
   __nv_bfloat16* gates[8];          // [T+1, B, 4H] (training)
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
@@ -103,11 +109,12 @@ static Work layout_work(char* base, const Dims& d, int training) {
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += al256(bytes); return p; };
   const size_t B = d.B, T = d.T, H = d.H, Ip0 = round8(d.I);
   w.cslots = training ? d.T + 1 : 2;
-  w.x_hi = (__nv_bfloat16*)take(T * B * Ip0 * 2);
-  w.x_lo = (__nv_bfloat16*)take(T * B * Ip0 * 2);
+  w.x_hi = (__half*)take(T * B * Ip0 * 2);
+  w.x_lo = (__half*)take(T * B * Ip0 * 2);
+  w.x_bf = (__nv_bfloat16*)take(T * B * Ip0 * 2);
   w.gin = (float*)take(T * B * 4 * H * 4);
   for (int l = 0; l < d.L; ++l) {
-    w.h_hi[l] = (__nv_bfloat16*)take((T + 1) * B * H * 2);
+    w.h_hi[l] = (__half*)take((T + 1) * B * H * 2);
     w.h_lo[l] = (__nv_bfloat16*)take((T + 1) * B * H * 2);
     w.c[l] = (float*)take((size_t)w.cslots * B * H * 4);
     w.gates[l] = training ? (__nv_bfloat16*)take((T + 1) * B * 4 * H * 2) : nullptr;
@@ -129,17 +136,18 @@ static Work layout_work(char* base, const Dims& d, int training) {
 
 // ------------------------------------------------------------------------------------------ input prep
 template <typename Tin>
-__global__ void prep_x_kernel(const Tin* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                              int B, int T, int I, int Ip) {
+__global__ void prep_x_kernel(const Tin* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                              __nv_bfloat16* __restrict__ bf, int B, int T, int I, int Ip) {
   const size_t n = (size_t)T * B * Ip;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int k = i % Ip;
     const size_t tb = i / Ip;
     const int b = tb % B, t = tb / B;
     const float v = k < I ? (float)x[((size_t)b * T + t) * I + k] : 0.f;   // x.float() (speech_embedder_net.py:28)
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __half h = __float2half_rn(v);
     hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    lo[i] = __float2half_rn(v - __half2float(h));
+    bf[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -167,50 +175,21 @@ __device__ __forceinline__ void lstm_cell8(const float (&pre)[32], const float (
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// h_t in both operand formats: fp16 (forward GEMMs) and bf16 (weight-gradient GEMMs)
 __device__ __forceinline__ void split_h8(const float (&hn)[8], uint4& hi, uint4& lo) {
   uint32_t hh[4], hl[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    hh[j] = pack_bf16x2(hn[2 * j], hn[2 * j + 1]);
-    hl[j] = pack_bf16x2(hn[2 * j] - bf16_lo_of(hh[j]), hn[2 * j + 1] - bf16_hi_of(hh[j]));
+    hh[j] = pack_f16x2(hn[2 * j], hn[2 * j + 1]);
+    hl[j] = pack_bf16x2(hn[2 * j], hn[2 * j + 1]);
   }
   hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
   lo = make_uint4(hl[0], hl[1], hl[2], hl[3]);
 }
-
-// Pointer-based cell (direct global stores); used by the persistent kernel in plstm.cuh.
-struct CellDirect {
-  struct Params {
-    const float* gin;          // [B, 4H] slice of step t
-    const float* c_prev;       // [B, H]
-    float* c_out;              // [B, H]
-    __nv_bfloat16* h_hi;       // [B, H] slot t+1
-    __nv_bfloat16* h_lo;       // nullable
-    __nv_bfloat16* gates;      // [B, 4H] slice of step t, nullable
-    float* h_f32;              // [B, H], nullable (top layer, last step)
-    int H;
-  };
-  static __device__ __forceinline__ void cell(const Params& p, int m, int n0, const float (&pre)[32], const float (&cp)[8]) {
-    const int u0 = (n0 >> 5) * 8;
-    const size_t hoff = (size_t)m * p.H + u0;
-    CellRegs r;
-    lstm_cell8(pre, cp, r);
-    *reinterpret_cast<float4*>(p.c_out + hoff) = make_float4(r.cn[0], r.cn[1], r.cn[2], r.cn[3]);
-    *reinterpret_cast<float4*>(p.c_out + hoff + 4) = make_float4(r.cn[4], r.cn[5], r.cn[6], r.cn[7]);
-    uint4 hi, lo;
-    split_h8(r.hn, hi, lo);
-    *reinterpret_cast<uint4*>(p.h_hi + hoff) = hi;
-    if (p.h_lo) *reinterpret_cast<uint4*>(p.h_lo + hoff) = lo;
-    if (p.h_f32) {
-      *reinterpret_cast<float4*>(p.h_f32 + hoff) = make_float4(r.hn[0], r.hn[1], r.hn[2], r.hn[3]);
-      *reinterpret_cast<float4*>(p.h_f32 + hoff + 4) = make_float4(r.hn[4], r.hn[5], r.hn[6], r.hn[7]);
-    }
-    if (p.gates) {
-      uint4* go4 = reinterpret_cast<uint4*>(p.gates + (size_t)m * 4 * p.H + n0);
-      go4[0] = pack8(r.gi); go4[1] = pack8(r.gf); go4[2] = pack8(r.gg); go4[3] = pack8(r.go);
-    }
-  }
-};
 
 // Forward frame epilogue (BN = 128 packed gate columns = 32 units): acc = W_hh h_{t-1}.
 // TMA-loaded inputs (swizzled smem): gin tile 4 x [128 rows x 32 fp32], c_{t-1} tile [128 x 32 fp32].
@@ -377,8 +356,6 @@ struct EpiLstmBwd {
     tma_store_3d(&p.t_dc, out + kOdc, n0, m0, 0);
   }
 };
-
-#include "plstm.cuh"
 
 // ------------------------------------------------------------------------------------------ projection + L2 norm
 // y[b,:] = W h_last[b,:] + bias; emb = y/|y|   (speech_embedder_net.py:31-32; fp32; 8 batch rows per CTA)
@@ -621,14 +598,14 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
   {
     const size_t n = (size_t)T * B * Ip0;
     const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    if (x_dtype == 0) prep_x_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), w.x_hi, w.x_lo, B, T, I, Ip0);
-    else if (x_dtype == 1) prep_x_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x), w.x_hi, w.x_lo, B, T, I, Ip0);
+    if (x_dtype == 0) prep_x_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), w.x_hi, w.x_lo, w.x_bf, B, T, I, Ip0);
+    else if (x_dtype == 1) prep_x_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x), w.x_hi, w.x_lo, w.x_bf, B, T, I, Ip0);
     else return SVB_ERR_ARG;
     SVB_CUDA("prep_x");
   }
   for (int l = 0; l < L; ++l) {
     cudaMemsetAsync(w.h_hi[l], 0, BH * 2, s);
-    cudaMemsetAsync(w.h_lo[l], 0, BH * 2, s);
+    if (training) cudaMemsetAsync(w.h_lo[l], 0, BH * 2, s);
     cudaMemsetAsync(w.c[l], 0, BH * 4, s);
     if (training) cudaMemsetAsync(w.gates[l] + (size_t)T * B * 4 * H, 0, (size_t)B * 4 * H * 2, s);
   }
@@ -637,14 +614,15 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     // ---- input projection over all frames: gin[T*B, 4H] = X W_ih^T + bias (3-term split bf16)
     prof_mark(PH_IN_GEMM, s);
     {
-      const __nv_bfloat16* xh = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;   // slots 1..T of the layer below
-      const __nv_bfloat16* xl = l == 0 ? w.x_lo : w.h_lo[l - 1] + BH;
+      // layer 0 (log-mel input, K = 40): x_hi W_hi + x_lo W_hi + x_hi W_lo; upper layers: h16 W16 (+ h16 W16_lo)
+      const __half* xh = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;          // slots 1..T of the layer below
       GemmOperands ops;
       memset(&ops, 0, sizeof(ops));
-      ops.nterms = 3; ops.M = T * B; ops.N = 4 * H; ops.K = lw.Ip;
-      const void* As[3] = {xh, xl, xh};
-      const void* Bs[3] = {lw.wih_hi, lw.wih_hi, lw.wih_lo};
-      for (int t = 0; t < 3; ++t) {
+      ops.f16 = 1;
+      ops.nterms = l == 0 ? 3 : (rec_terms >= 2 ? 2 : 1); ops.M = T * B; ops.N = 4 * H; ops.K = lw.Ip;
+      const void* As[3] = {xh, l == 0 ? (const void*)w.x_lo : (const void*)xh, xh};
+      const void* Bs[3] = {lw.wih_hi, l == 0 ? lw.wih_hi : lw.wih_lo, lw.wih_lo};
+      for (int t = 0; t < ops.nterms; ++t) {
         SVB_TRY(make_operand_map(&ops.ta[t], As[t], T * B, lw.Ip, lw.Ip, 0, kBM));
         SVB_TRY(make_operand_map(&ops.tb[t], Bs[t], 4 * H, lw.Ip, lw.Ip, 0, 128));
       }
@@ -656,38 +634,12 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
       if (e != cudaSuccess) { set_error("input projection", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_REC_FWD, s);
-    // ---- recurrence, persistent form: one cooperative launch per (layer, <=6 batch tiles) runs all T frames
-    if (g_persistent && rec_terms == 1 && (H == 768 || H == 512 || H == 256)) {
-      static int num_sms = 0;
-      if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-      const int max_tiles = num_sms / (H / 32) < 64 ? num_sms / (H / 32) : 64;
-      if (max_tiles >= 1) {
-        PlstmParams pp;
-        memset(&pp, 0, sizeof(pp));
-        SVB_TRY(make_operand_map(&pp.tw, lw.whh_hi, 4 * H, H, H, 0, 128));
-        pp.h_hi = w.h_hi[l]; pp.h_hi_w = w.h_hi[l];
-        pp.h_lo = (l + 1 < L) ? w.h_lo[l] : nullptr;
-        pp.gin = w.gin; pp.c = w.c[l]; pp.gates = training ? w.gates[l] : nullptr;
-        pp.h_last = (l == L - 1) ? w.h_last : nullptr;
-        pp.B = B; pp.T = T; pp.training = training;
-        const int tiles = (B + kBM - 1) / kBM;
-        for (int tile0 = 0; tile0 < tiles; tile0 += max_tiles) {
-          const int nt = tiles - tile0 < max_tiles ? tiles - tile0 : max_tiles;
-          pp.counters = w.counters + l * 64;
-          cudaMemsetAsync(pp.counters, 0, 64 * sizeof(unsigned), s);
-          pp.row0 = tile0 * kBM;
-          pp.rows = (B - pp.row0) < nt * kBM ? (B - pp.row0) : nt * kBM;
-          int e = H == 768 ? launch_plstm_fwd<768>(pp, nt, s) : H == 512 ? launch_plstm_fwd<512>(pp, nt, s) : launch_plstm_fwd<256>(pp, nt, s);
-          SVB_TRY(e);
-        }
-        continue;
-      }
-    }
     // ---- recurrence, per-frame form: one fused GEMM + cell kernel per frame (any H % 128 == 0, split terms)
     GemmOperands ops;
     memset(&ops, 0, sizeof(ops));
-    // terms: h_hi W_hi (+ h_hi W_lo (+ h_lo W_hi)): rec_terms > 1 buys accuracy for large-magnitude weights
-    ops.nterms = rec_terms; ops.M = B; ops.N = 4 * H; ops.K = H;
+    // terms: h16 W16 (+ h16 W16_lo): rec_terms > 1 buys accuracy for large-magnitude weights
+    ops.f16 = 1;
+    ops.nterms = rec_terms >= 2 ? 2 : 1; ops.M = B; ops.N = 4 * H; ops.K = H;
     // rec_terms == 1: CTA pairs (two 128-row batch tiles share each W_hh slice, 64 rows per CTA)
     // (pays off once the batch spans several waves of CTAs: extraction batches; at B = 640 the two cluster barriers
     //  per frame cost more than the halved W_hh traffic saves)
@@ -696,8 +648,6 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     SVB_TRY(make_operand_map(&ops.tb[0], lw.whh_hi, 4 * H, H, H, 0, fwd_pair ? 64 : 128));
     ops.ta[1] = ops.ta[0];
     SVB_TRY(make_operand_map(&ops.tb[1], lw.whh_lo, 4 * H, H, H, 0, 128));
-    SVB_TRY(make_tmap_bf16(&ops.ta[2], w.h_lo[l], H, B, T + 1, H, BH, kBM));
-    ops.tb[2] = ops.tb[0];
     EpiLstmFwd::Params ep;
     memset(&ep, 0, sizeof(ep));
     const int cslots = training ? T + 1 : 2;
@@ -706,7 +656,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     SVB_TRY(make_tmap(&ep.t_hhi, w.h_hi[l], 2, H, B, T + 1, H, BH, 32, 128, 0));
     SVB_TRY(make_tmap(&ep.t_hlo, w.h_lo[l], 2, H, B, T + 1, H, BH, 32, 128, 0));
     if (training) SVB_TRY(make_tmap(&ep.t_gates, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, 128, 3));
-    ep.has_hlo = (l + 1 < L || rec_terms > 2) ? 1 : 0;
+    ep.has_hlo = training ? 1 : 0;            // bf16 copy of h: only the weight-gradient GEMMs read it
     ep.has_gates = training ? 1 : 0;
     ep.H = H;
     for (int t = 0; t < T; ++t) {
@@ -775,14 +725,14 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       else SVB_TRY((launch_step<EpiLstmBwd, 32, 6, false, 4>(ops, ep, s)));
     }
     // ---- weight gradients: dW[4H, K] = dG^T X over all T*B rows (both operands MN-major), rows unpacked on store
-    const __nv_bfloat16* xin = l == 0 ? w.x_hi : w.h_hi[l - 1] + BH;
+    const __nv_bfloat16* xin = l == 0 ? w.x_bf : w.h_lo[l - 1] + BH;
     prof_mark(PH_WGRAD, s);
     {
       GemmOperands g;
       memset(&g, 0, sizeof(g));
       g.nterms = 1; g.M = 4 * H; g.N = H; g.K = TB;
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], 4 * H, TB, 4 * H, 1, 0));
-      SVB_TRY(make_operand_map(&g.tb[0], w.h_hi[l], H, TB, H, 1, 0));           // h_{t-1}: slots 0..T-1
+      SVB_TRY(make_operand_map(&g.tb[0], w.h_lo[l], H, TB, H, 1, 0));           // h_{t-1} (bf16): slots 0..T-1
       cudaError_t e;
       if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
         EpiStoreF32<128>::Params ep;
@@ -829,10 +779,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         SVB_TRY(make_store_params<256>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
         e = launch_tc_gemm<256, 6, false, false, EpiStoreF32<256>, 8, 1, true>(g, ep, s);
       } else {
-        SVB_TRY(make_operand_map(&g.tb[0], lw.wih_hi, H, 4 * H, lw.Ip, 1, 0));
+        SVB_TRY(make_operand_map(&g.tb[0], lw.wihT, H, 4 * H, 4 * H, 0, 128));
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, w.dh_above, nullptr, TB, H, (int64_t)H, 0));
-        e = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>, 8>(g, ep, s);
+        e = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>, 8>(g, ep, s);
       }
       if (e != cudaSuccess) { set_error("dX", e); return SVB_ERR_CUDA; }
     }

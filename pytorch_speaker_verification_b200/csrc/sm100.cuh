@@ -211,6 +211,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn, i
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
+// Same with IEEE half operands (A/B format 0 = F16): 11 significant bits instead of 8.  The forward LSTM GEMMs use
+// it (|h| < 1, |W| << 65504): the embedding error drops from 5e-4 (split-bf16 x3 input projection + bf16
+// recurrence) to 2e-4 with a single term everywhere (scripts/precision_study.py).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) |
+         (uint32_t(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {

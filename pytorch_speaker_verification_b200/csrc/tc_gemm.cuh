@@ -30,6 +30,7 @@ struct __align__(64) GemmOperands {
   int za[kMaxTerms];             // slab (3rd tensor-map coordinate) of A per term
   int zb[kMaxTerms];
   int nterms;
+  int f16;                       // operands are IEEE half instead of bf16 (same tensor maps: 2-byte elements)
   int M, N, K;                   // K = reduction length per term
   unsigned long long* trace;     // debug: 16 globaltimer stamps per CTA, or null
 };
@@ -184,7 +185,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(TWO_CTA ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t idesc = ops.f16 ? umma_idesc_f16(TWO_CTA ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                   : umma_idesc_bf16(TWO_CTA ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < (TWO_CTA && pair_rank != 0 ? 0 : iters); ++it) {
