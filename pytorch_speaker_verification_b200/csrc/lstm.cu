@@ -98,7 +98,9 @@ struct Work {
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
   float *dh_above, *dc, *dh_last, *dy;  // backward: [T,B,H], [B,H], [B,H], [B,P]
   float* colsum_part;               // [chunks, 4H]
-  unsigned* counters;               // [L][64] frame counters of the persistent kernel
+  float* gin_ring[8];               // persistent kernel: [kWlGinRing][nt][H/32][64 x 128] fp32 per layer
+  unsigned *hcnt, *gcnt;            // persistent kernel: [L][nt] and [L][H/32][nt] progress counters
+  size_t cnt_bytes;
   int cslots;
   size_t bytes;
 };
@@ -122,7 +124,13 @@ static Work layout_work(char* base, const Dims& d, int training) {
   w.h_last = (float*)take(B * H * 4);
   w.y = (float*)take(B * d.P * 4);
   w.inv_norm = (float*)take(B * 4);
-  w.counters = (unsigned*)take(8 * 64 * 4);
+  {
+    const size_t nt = (B + 63) / 64, NS = H / 32;
+    for (int l = 0; l < d.L; ++l) w.gin_ring[l] = (float*)take((size_t)3 * nt * NS * 8192 * 4);
+    w.cnt_bytes = al256((size_t)d.L * nt * 4) + al256((size_t)d.L * NS * nt * 4);
+    w.hcnt = (unsigned*)take(w.cnt_bytes);
+    w.gcnt = w.hcnt + al256((size_t)d.L * nt * 4) / 4;
+  }
   if (training) {
     w.dh_above = (float*)take(T * B * H * 4);
     w.dc = (float*)take(B * H * 4);
@@ -357,6 +365,9 @@ struct EpiLstmBwd {
   }
 };
 
+#include "wlstm.cuh"
+static_assert(kWlGinRing == 3, "layout_work sizes the gin ring for 3 frames");
+
 // ------------------------------------------------------------------------------------------ projection + L2 norm
 // y[b,:] = W h_last[b,:] + bias; emb = y/|y|   (speech_embedder_net.py:31-32; fp32; 8 batch rows per CTA)
 constexpr int kProjRows = 8;
@@ -509,9 +520,10 @@ struct Profiler {
   int created = 0;
 };
 static Profiler g_prof;
-static int g_persistent = 0;
+static int g_persistent = 1;   // persistent wavefront forward kernel (wlstm.cuh) when the shape allows
 static int g_fwd_pair = 0;     // forward frame: CTA pairs share the W_hh slice (measured slower: cluster barriers outweigh the ingest saving)
 static int g_bwd_splitk = 1;   // BPTT frame: 4-CTA cluster split-K with DSMEM partial exchange
+static int g_ablate = 0;      // debug: persistent kernel ablation mask (timing experiments only)
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
 static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
   if (!g_prof.on || g_prof.n >= 256) return;
@@ -545,6 +557,7 @@ using namespace svb;
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
 extern "C" int svb_set_fwd_pair(int on) { g_fwd_pair = on != 0; return SVB_OK; }
 extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
+extern "C" int svb_set_ablate(int mask) { g_ablate = mask; return SVB_OK; }
 extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
 extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
 // Sums the elapsed ms per phase since the last enable/read; the caller must have synchronised the stream.
@@ -609,9 +622,42 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     cudaMemsetAsync(w.c[l], 0, BH * 4, s);
     if (training) cudaMemsetAsync(w.gates[l] + (size_t)T * B * 4 * H, 0, (size_t)B * 4 * H * 2, s);
   }
-  for (int l = 0; l < L; ++l) {
+  bool use_wlstm = false;
+  if (g_persistent && rec_terms == 1 && L <= 3 && (H == 768 || H == 512 || H == 256)) {
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    use_wlstm = 2 * L * (H / 32) <= num_sms;
+  }
+  if (use_wlstm) {
+    // ---- whole LSTM stack in one persistent wavefront kernel (weights stationary in tensor memory)
+    prof_mark(PH_REC_FWD, s);
+    const int nt = (B + kWlTile - 1) / kWlTile;
+    const int cslots = training ? T + 1 : 2;
+    WlstmParams wp;
+    memset(&wp, 0, sizeof(wp));
+    for (int l = 0; l < L; ++l) {
+      const LayerW& lw = pw.l[l];
+      WlstmLayer& ly = wp.layer[l];
+      if (l == 0) SVB_TRY(make_tmap(&ly.t_in, w.x_hi, 2, Ip0, B, T, Ip0, (uint64_t)B * Ip0, 64, kWlTile, 3));
+      else SVB_TRY(make_tmap(&ly.t_in, w.h_hi[l - 1], 2, H, B, T + 1, H, BH, 64, kWlTile, 3));
+      SVB_TRY(make_tmap(&ly.t_h, w.h_hi[l], 2, H, B, T + 1, H, BH, 64, kWlTile, 3));
+      SVB_TRY(make_tmap(&ly.t_h16_st, w.h_hi[l], 2, H, B, T + 1, H, BH, 32, kWlTile, 0));
+      SVB_TRY(make_tmap(&ly.t_hbf_st, w.h_lo[l], 2, H, B, T + 1, H, BH, 32, kWlTile, 0));
+      SVB_TRY(make_tmap(&ly.t_c, w.c[l], 4, H, B, cslots, H, BH, 32, kWlTile, 3));
+      if (training) SVB_TRY(make_tmap(&ly.t_gates, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, kWlTile, 3));
+      ly.whh = lw.whh_hi; ly.wih = lw.wih_hi; ly.bias = lw.bias; ly.gin = w.gin_ring[l];
+      ly.Ip = lw.Ip; ly.in_slab0 = l == 0 ? 0 : 1;
+    }
+    wp.hcnt = w.hcnt; wp.gcnt = w.gcnt; wp.h_last = w.h_last;
+    wp.trace = reinterpret_cast<long long*>(g_trace);
+    wp.ablate = g_ablate;
+    wp.B = B; wp.T = T; wp.L = L; wp.H = H; wp.nt = nt; wp.training = training;
+    cudaMemsetAsync(w.hcnt, 0, w.cnt_bytes, s);
+    SVB_TRY(H == 768 ? launch_wlstm_fwd<768>(wp, s) : H == 512 ? launch_wlstm_fwd<512>(wp, s) : launch_wlstm_fwd<256>(wp, s));
+  }
+  for (int l = 0; l < L && !use_wlstm; ++l) {
     const LayerW& lw = pw.l[l];
-    // ---- input projection over all frames: gin[T*B, 4H] = X W_ih^T + bias (3-term split bf16)
+    // ---- input projection over all frames: gin[T*B, 4H] = X W_ih^T + bias (layer 0: 3-term split fp16)
     prof_mark(PH_IN_GEMM, s);
     {
       // layer 0 (log-mel input, K = 40): x_hi W_hi + x_lo W_hi + x_hi W_lo; upper layers: h16 W16 (+ h16 W16_lo)

@@ -1,0 +1,541 @@
+// Persistent wavefront LSTM forward kernel: weights stationary in TENSOR MEMORY (included by lstm.cu, namespace svb).
+//
+// Replaces, for the whole stack at once, nn.LSTM's forward (speech_embedder_net.py:19,28): one launch runs all T
+// frames of all L layers.  2*L*(H/32) CTAs (144 at L=3, H=768), one per SM, two roles:
+//
+//   R(l, n)  recurrence of layer l, gate-column slice n (128 packed gate columns = 32 hidden units x 4 gates):
+//            W_hh[slice] (128 x H fp16 = 192 KB at H=768) is loaded ONCE into tensor memory as the A operand of
+//            tcgen05.mma (TS form).  Per frame t and 64-row batch tile j the CTA streams h^l_{t-1}[tile j] (K-major
+//            fp16, TMA -> 128B-swizzled smem ring) as the B operand, so the accumulator is TRANSPOSED:
+//            D[gate column (TMEM lane), batch row (TMEM column)].  Epilogue: + gin (from P(l, n)), sigma/tanh of the
+//            thread's own gate column, a 4x4 register transpose across the four gate lanes of a unit (shuffles),
+//            the cell update, and TMA stores of h_t (fp16 + bf16), c_t and the gate stash for BPTT.
+//   P(l, n)  input projection of layer l, same slice: W_ih[slice] resident in tensor memory, streams
+//            x_t (l = 0) or h^{l-1}_t (l > 0), writes gin = W_ih x + b_ih + b_hh (fp32) to a small L2-resident ring in
+//            the epilogue's own fragment order (coalesced 16-byte stores/loads, no staging).
+//
+// Nothing is re-read per frame except the activations themselves: per frame a CTA pulls B*K*2 bytes (0.98 MB) and
+// no weights, where the per-frame kernels pulled 393 KB of W_hh per 128x128 tile per frame (L2-throughput bound).
+// Shared memory is free for a deep operand ring and double-buffered TMA staging.
+//
+// Ordering is by monotonically increasing counters in global memory (release/acquire at gpu scope), no grid barrier:
+//   hcnt[l][j]     += 1 by every R(l, .) after its stores of (t, j) completed  -> h^l_t[tile j] complete at NS*(t+1)
+//   gcnt[l][n][j]   = t+1 by P(l, n) after gin of (t, j) is written
+// R(l,t,j) waits hcnt[l][j] >= NS*t and gcnt[l][n][j] >= t+1; P(l,t,j) waits hcnt[l-1][j] >= NS*(t+1) and (ring
+// back-pressure) hcnt[l][j] >= NS*(t-D+1).  The dependency graph is acyclic in (t, l) and all CTAs are co-resident
+// (cooperative launch), so the layers form a self-timed wavefront: layer l runs frame t while layer l+1 runs t-1.
+// TMEM map (512 columns): [0, K/2) = weights, two fp16 per column; [384, 448) and [448, 512) = two accumulators.
+#pragma once
+
+constexpr int kWlTile = 64;            // batch rows per tile (= MMA N)
+// 64-wide K blocks per ring stage.  An mbarrier try_wait costs ~170 cycles even when the phase is already complete
+// (scripts/ubench/mma_issue.cu) and the tensor pipe drains meanwhile (tcgen05.mma issue behaves like a depth-1
+// queue), so waits must be rare: 6 K blocks = 24 MMAs of N = 64 (768 cycles of tensor work) per wait.
+constexpr int kWlKbPerStage = 6;
+constexpr int kWlStages = 3;           // operand ring: 3 x 6 x [64 rows x 64 K] fp16 = 144 KB (1.5 tiles in flight)
+constexpr int kWlKbBytes = kWlTile * 128;
+constexpr int kWlStageBytes = kWlKbPerStage * kWlKbBytes;
+constexpr int kWlGinRing = 3;          // frames of gin kept in flight per layer
+constexpr int kWlDeps = 4;             // tiles the dependency poller may run ahead
+constexpr int kWlEpiWarps = 16;        // four warps per TMEM lane quarter, 16 batch rows of the tile each
+// Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer, 18 store/signal, 19 dependency poller.  The single-thread
+// roles get the HIGHEST warp ids: the SM sub-partition arbiter prefers the highest warp id among eligible warps, and
+// as warp 1 the MMA issuer starved behind the four MUFU-heavy epilogue warps of its sub-partition (94 instead of 32
+// cycles per tcgen05.mma, tensor pipe 31 % busy).
+constexpr int kWlThreads = 32 * kWlEpiWarps + 128;
+constexpr int kWlWarpTma = kWlEpiWarps, kWlWarpMma = kWlEpiWarps + 1, kWlWarpStore = kWlEpiWarps + 2,
+              kWlWarpPoll = kWlEpiWarps + 3;   // lane 0: dependency poller, lane 1: c tile loader
+constexpr int kWlAccCol = 384;
+// staging buffer (per accumulator buffer): c tile (in place), h fp16, h bf16, two gate boxes
+constexpr int kWlOffC = 0, kWlOffH16 = 8192, kWlOffHbf = 12288, kWlOffG = 16384, kWlStgBytes = 32768;
+constexpr int kWlCinBytes = 8192;      // c_{t-1} tile, loaded ahead of time (double-buffered)
+constexpr int kWlSmem = kWlStages * kWlStageBytes + 2 * kWlStgBytes + 2 * kWlCinBytes + 1024 + 1024;
+
+struct __align__(64) WlstmLayer {
+  CUtensorMap t_in;        // B operand of P: fp16 x [T][B][Ip] (l = 0) or h^{l-1} [T+1][B][H]; box {64, 64} SW128
+  CUtensorMap t_h;         // B operand of R: fp16 h^l [T+1][B][H]; box {64, 64} SW128
+  CUtensorMap t_h16_st;    // store h^l fp16, box {32, 64}, no swizzle
+  CUtensorMap t_hbf_st;    // store h^l bf16 (training)
+  CUtensorMap t_c;         // fp32 c [cslots][B][H], box {32, 64} SW128, load + store
+  CUtensorMap t_gates;     // bf16 gates [T+1][B][4H], box {64, 64} SW128, store (training)
+  const __half* whh;       // packed [4H][H]
+  const __half* wih;       // packed [4H][Ip]
+  const float* bias;       // packed [4H]
+  float* gin;              // ring [kWlGinRing][nt][NS][64 x 128] fp32, fragment order
+  int Ip;                  // K of the input projection (row pitch of wih)
+  int in_slab0;            // slab of t_in that holds frame 0 (0 for x, 1 for h of the layer below)
+};
+struct __align__(64) WlstmParams {
+  WlstmLayer layer[3];
+  unsigned* hcnt;          // [L][nt]
+  unsigned* gcnt;          // [L][NS][nt]
+  float* h_last;           // [B][H] fp32: top layer, last frame
+  long long* trace;        // debug: clock64 stamps of R(1,0) and P(1,0) at frame T/2 ([2][nt][16]), or null
+  int B, T, L, H, nt, training;
+  int ablate;              // debug: 1 skip MMAs, 2 skip epilogue math, 4 skip operand loads (results are garbage)
+};
+#define WL_STAMP(slot) do { if (tr) tr[(slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Spin until *a >= ta and *b >= tb (null pointer = no condition); both loads are in flight together.  Bounded: a lost
+// arrival traps instead of hanging the GPU.
+// NO acquire / proxy fence follows on purpose.  Everything that is read after the flag bypasses L1 (TMA loads and
+// ld.global.cg go to L2, the point of coherence) and is issued only after the flag value has come back (the poller
+// arrives on an mbarrier that the consumers wait on), and the writers completed their data at L2 before raising the
+// flag (TMA stores: cp.async.bulk.wait_group; gin: fence.acq_rel.gpu in the signal warp).  fence.acq_rel.gpu and
+// fence.proxy.async cost ~1000 cycles EACH here and made this loop (3 fences per tile) the limiter of the whole
+// kernel: 2.2 us per tile with all math, loads and stores switched off.
+__device__ __forceinline__ void wait_two_counters(const unsigned* a, unsigned ta, const unsigned* b, unsigned tb) {
+  long long t0 = 0;
+  while (true) {
+    const unsigned va = a ? ld_relaxed(a) : ta;
+    const unsigned vb = b ? ld_relaxed(b) : tb;
+    if (va >= ta && vb >= tb) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) {
+      printf("svb: wlstm dependency timeout cta %d have (%u, %u) want (%u, %u)\n", blockIdx.x, va, vb, ta, tb);
+      __trap();
+    }
+  }
+}
+
+template <int H>
+__global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_constant__ WlstmParams p) {
+  constexpr int NS = H / 32;                 // gate-column slices per layer
+  constexpr int NKB_R = H / 64;
+  static_assert(H % 64 == 0 && H / 2 <= kWlAccCol, "hidden size does not fit the tensor-memory weight slice");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* stg = smem + kWlStages * kWlStageBytes;
+  uint8_t* cin = stg + 2 * kWlStgBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(cin + 2 * kWlCinBytes);
+  uint64_t* empty = full + kWlStages;
+  uint64_t* acc_full = empty + kWlStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* cin_full = acc_empty + 2;          // [2]
+  uint64_t* stg_full = cin_full + 2;           // [2]
+  uint64_t* stg_free = stg_full + 2;           // [2]
+  uint64_t* dep_ready = stg_free + 2;          // [kWlDeps]
+  uint64_t* dep_free = dep_ready + kWlDeps;    // [kWlDeps]
+  uint64_t* gin_done = dep_free + kWlDeps;     // [2] (P: gin tile written by all epilogue threads)
+  uint64_t* gin_taken = gin_done + 2;          // [2] (P: the signal warp has seen gin_done; keeps the phases apart)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(gin_taken + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const bool is_R = cta < p.L * NS;
+  const int l = (is_R ? cta : cta - p.L * NS) / NS;
+  const int n = (is_R ? cta : cta - p.L * NS) % NS;
+  const WlstmLayer& ly = p.layer[l];
+  const int K = is_R ? H : ly.Ip;
+  const int nkb = is_R ? NKB_R : (K + 63) / 64;
+  const int ngroups = (nkb + kWlKbPerStage - 1) / kWlKbPerStage;
+  const int nt = p.nt, T = p.T;
+  const long long total = (long long)T * nt;
+  long long* const trace_cta = (p.trace && l == 1 && n == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWlStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kWlEpiWarps / 2);        // one epilogue group (8 warps) per accumulator buffer
+      mbar_init(&cin_full[b], 1);
+      mbar_init(&stg_full[b], 16 * kWlEpiWarps);
+      mbar_init(&stg_free[b], 1);
+      mbar_init(&gin_done[b], 16 * kWlEpiWarps);
+      mbar_init(&gin_taken[b], 1);
+    }
+    for (int d = 0; d < kWlDeps; ++d) {
+      mbar_init(&dep_ready[d], 1);
+      mbar_init(&dep_free[d], is_R ? 2 + kWlEpiWarps / 2 : 1); // the producer (+ c loader + one epilogue group of R)
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(is_R ? &ly.t_h : &ly.t_in);
+  }
+  if (warp == kWlWarpMma) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  // ---- weights -> tensor memory (once): lane r = packed gate row 128 n + r, two fp16 per column
+  if (warp < 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const __half* wrow = (is_R ? ly.whh : ly.wih) + (size_t)(n * 128 + r) * K;
+    for (int kb = 0; kb < nkb; ++kb) {
+      uint32_t v[32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (kb * 64 + u * 8 < K) x = __ldg(reinterpret_cast<const uint4*>(wrow + kb * 64 + u * 8));   // K % 8 == 0
+        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+      }
+      tmem_st32(tmem + (uint32_t(q * 32) << 16) + kb * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kWlWarpPoll && lane == 0) {
+    // ------------------------------------------------------------------ dependency poller (runs ahead of the rest)
+    // A satisfied poll still costs an L2 round trip (~1000 clk); here it overlaps the previous tiles' work.
+    {
+      long long it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int d = (int)(it % kWlDeps);
+          mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1));
+          if (is_R) {
+            wait_two_counters(t > 0 ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * t),
+                              p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
+          } else {
+            wait_two_counters(l > 0 ? p.hcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (t + 1)),
+                              t >= kWlGinRing ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * (t - kWlGinRing + 1)));
+          }
+          mbar_arrive(&dep_ready[d]);
+        }
+      }
+    }
+  } else if (warp == kWlWarpPoll && lane == 1) {
+    // ------------------------------------------------------------------ c_{t-1} tile loader (R only)
+    // Its own thread: the wait for the c buffer (epilogue of tile it-2 finished) must not hold back the operand
+    // loads of later tiles, or load latency + MMA + epilogue chain up into the per-tile period.
+    if (is_R) {
+      long long it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          const int d = (int)(it % kWlDeps);
+          mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));   // our own stores of frame t-1 are complete
+          mbar_arrive(&dep_free[d]);
+          mbar_wait(&stg_full[buf], upar ^ 1);                       // the epilogue of tile it-2 has read its c tile
+          mbar_expect_tx(&cin_full[buf], kWlCinBytes);
+          tma_load_3d(cin + buf * kWlCinBytes, &ly.t_c, &cin_full[buf], n * 32, j * kWlTile, p.training ? t : (t & 1));
+        }
+      }
+    }
+  } else if (warp == kWlWarpTma) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          const int d = (int)(it % kWlDeps);
+          long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
+          WL_STAMP(0);
+          mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));
+          mbar_arrive(&dep_free[d]);
+          WL_STAMP(1);
+          const CUtensorMap* tm = is_R ? &ly.t_h : &ly.t_in;
+          const int slab = is_R ? t : t + ly.in_slab0;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            const int kb0 = gi * kWlKbPerStage;
+            const int nk = nkb - kb0 < kWlKbPerStage ? nkb - kb0 : kWlKbPerStage;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (p.ablate & 4) {
+              mbar_arrive(&full[stage]);
+              if (++stage == kWlStages) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            mbar_expect_tx(&full[stage], nk * kWlKbBytes);
+            for (int k = 0; k < nk; ++k)
+              tma_load_3d(ring + stage * kWlStageBytes + k * kWlKbBytes, tm, &full[stage], (kb0 + k) * 64, j * kWlTile, slab);
+            if (tr && gi < 3) tr[3 * nt * 16 + 13 + gi] = clock64();   // issue time of groups 0..2
+            if (++stage == kWlStages) { stage = 0; phase ^= 1; }
+          }
+          WL_STAMP(2);
+        }
+      }
+    }
+  } else if (warp == kWlWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (A = weights in TMEM)
+    constexpr uint32_t idesc = umma_idesc_f16(128, kWlTile, 0, 0);
+    const uint64_t desc0 = umma_desc_kmajor_sw128(smem_u32(ring));
+    const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
+    int stage = 0;
+    uint32_t phase = 0;
+    // ONE thread runs the whole loop (waits included): looping the whole warp with an election and a __syncwarp per
+    // group costs +150 cycles per group of 8 MMAs (256 cycles of tensor work), scripts/ubench/mma_issue.cu
+    const long long my_total = elect_one() ? total : 0;
+    for (long long it = 0; it < my_total; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t upar = (uint32_t)((it >> 1) & 1);
+      long long* tr = (trace_cta && it / nt == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;
+      WL_STAMP(3);
+      mbar_wait(&acc_empty[buf], upar ^ 1);
+      tc_fence_after();
+      WL_STAMP(4);
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int kb0 = gi * kWlKbPerStage;
+        const int nk = nkb - kb0 < kWlKbPerStage ? nkb - kb0 : kWlKbPerStage;
+        long long* trd = tr ? tr + 3 * nt * 16 : nullptr;      // MMA detail rows
+        if (trd && gi < 6) trd[2 * gi] = clock64();
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (trd && gi < 6) trd[2 * gi + 1] = clock64();
+        if (gi == 0) WL_STAMP(5);
+        if (gi == ngroups - 1) WL_STAMP(6);
+        {
+          // descriptor of stage s, K block kk, K step k = desc0 + ((s * stage + kk * 8192 + k * 32) >> 4) in the low half
+          const uint32_t lo = desc_lo0 + stage * (kWlStageBytes >> 4);
+          const uint32_t a0 = tmem + kb0 * 32;
+          const uint32_t dacc = tmem + kWlAccCol + buf * kWlTile;
+          if (p.ablate & 1) {
+          } else if (nk == kWlKbPerStage) {
+#pragma unroll
+            for (int q = 0; q < 4 * kWlKbPerStage; ++q)
+              umma_f16_ts_lohi(dacc, a0 + q * 8, lo + (q >> 2) * (kWlKbBytes >> 4) + (q & 3) * 2, desc_hi, idesc,
+                               q == 0 ? (gi != 0 ? 1u : 0u) : 1u);
+          } else {
+            for (int q = 0; q < 4 * nk; ++q)
+              umma_f16_ts_lohi(dacc, a0 + q * 8, lo + (q >> 2) * (kWlKbBytes >> 4) + (q & 3) * 2, desc_hi, idesc,
+                               (gi | q) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (gi == ngroups - 1) umma_commit(&acc_full[buf]);
+          if (trd && gi == ngroups - 1) trd[12] = clock64();
+        }
+        if (++stage == kWlStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < kWlEpiWarps) {
+    // ------------------------------------------------------------------ epilogue: thread = gate column (TMEM lane)
+    // Two groups of 8 warps work on alternate tiles (group = accumulator buffer), so that one group's MUFU-bound
+    // activation phase overlaps the other's shuffle / shared-memory phases and the ~170-cycle mbarrier waits.
+    // Within a group two warps share a TMEM lane quarter; each takes two 16-row parts of the 64-row tile.
+    const int grp = warp >> 3;                 // tiles it = grp, grp + 2, ... (accumulator / staging buffer = grp)
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int sub = (warp >> 2) & 1;           // parts sub and sub + 2: rows [16 part, 16 part + 16)
+    const int col = q * 32 + lane;             // packed gate column within the slice
+    const int g = lane >> 3, ju = lane & 7;    // gate (i, f, g, o) and unit within the warp's 8 units
+    const int unit = q * 8 + ju;               // unit within the CTA's 32
+    const bool g0 = g & 1, g1 = g >> 1;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const float bias = is_R ? 0.f : __ldg(ly.bias + n * 128 + col);
+    // activation of this thread's gate with one MUFU.TANH: sigmoid(x) = 0.5 tanh(0.5 x) + 0.5  (2^-11 relative:
+    // embedding error 3.3e-4 instead of 2.3e-4 in the emulation of scripts/precision_study.py)
+    const float cs = g == 2 ? 1.0f : 0.5f, ca = g == 2 ? 1.0f : 0.5f, cb = g == 2 ? 0.0f : 0.5f;
+    const int buf = grp;
+    // shared-memory addresses of this thread's slots, swizzle terms folded in (row & 7 is known at compile time below)
+    const uint32_t sb_a = smem_u32(stg) + buf * kWlStgBytes;
+    const int cb2 = (q & 1) * 32 + lane;                               // column within the 64-column gate box
+    uint32_t gbase[8];                                                 // gate stash: row i -> gbase[i & 7] + i * 128
+#pragma unroll
+    for (int m = 0; m < 8; ++m) gbase[m] = sb_a + kWlOffG + (q >> 1) * 8192 + (((cb2 >> 3) ^ m) << 4) + (cb2 & 7) * 2;
+    uint32_t cx[2];                                                    // c tile: row 4k + g -> cx[k & 1] + k * 512
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cx[e] = g * 128 + ((((unit >> 2) ^ ((e << 2) | g))) << 4) + (unit & 3) * 4;
+    const uint32_t cin_a = smem_u32(cin) + buf * kWlCinBytes;
+    const uint32_t hx = g * 64 + unit * 2;                             // h tiles: row 4k + g -> hx + k * 256
+    for (long long it = grp; it < total; it += 2) {
+      const int t = (int)(it / nt), j = (int)(it % nt);
+      const uint32_t upar = (uint32_t)((it >> 1) & 1);
+      float4* gfrag = reinterpret_cast<float4*>(ly.gin) + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 2048 + col;
+      float4 gv[2][4];
+      long long* tr = (trace_cta && t == T / 2 && (warp & 7) == 0 && lane == 0) ? trace_cta + j * 16 : nullptr;
+      WL_STAMP(7);
+      if (is_R) {
+        const int d = (int)(it % kWlDeps);
+        mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));     // gin of (t, j) is published
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gv[ps][k] = __ldcg(gfrag + ((sub + 2 * ps) * 4 + k) * 128);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dep_free[d]);
+      }
+      WL_STAMP(8);
+      mbar_wait(&acc_full[buf], upar);
+      tc_fence_after();
+      WL_STAMP(9);
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        const int part = sub + 2 * ps;
+        float acc[16];
+        tmem_ld16(tmem + lane_base + kWlAccCol + buf * kWlTile + part * 16, acc);
+        tmem_ld_wait();
+        if (ps == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (!is_R) {
+          // gin = W_ih x + bias, in fragment order: float4 (rows 4r..4r+3) of column `col` at [r][col]
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            gfrag[(part * 4 + k) * 128] = make_float4(acc[4 * k] + bias, acc[4 * k + 1] + bias, acc[4 * k + 2] + bias,
+                                                      acc[4 * k + 3] + bias);
+          continue;
+        }
+        if (p.ablate & 2) continue;
+        // ---- activations of this thread's gate column for 16 rows
+        float a[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[4 * k + 0] = fmaf(ca, tanh_approx((acc[4 * k + 0] + gv[ps][k].x) * cs), cb);
+          a[4 * k + 1] = fmaf(ca, tanh_approx((acc[4 * k + 1] + gv[ps][k].y) * cs), cb);
+          a[4 * k + 2] = fmaf(ca, tanh_approx((acc[4 * k + 2] + gv[ps][k].z) * cs), cb);
+          a[4 * k + 3] = fmaf(ca, tanh_approx((acc[4 * k + 3] + gv[ps][k].w) * cs), cb);
+        }
+        if (ps == 0) {
+          WL_STAMP(10);
+          mbar_wait(&stg_free[buf], upar ^ 1);    // staging buffer drained by the store warp
+          WL_STAMP(11);
+        }
+        if (p.training) {
+          // gate stash [row][packed col] bf16: two boxes of 64 columns, 128B-swizzled rows
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const uint32_t pk = pack_bf16x2(a[i], a[i + 1]);
+            sts_u16(gbase[i & 7] + part * 2048 + i * 128, (uint16_t)(pk & 0xffffu));
+            sts_u16(gbase[(i + 1) & 7] + part * 2048 + (i + 1) * 128, (uint16_t)(pk >> 16));
+          }
+        }
+        // 4 x 4 transposes across the lanes (g, ju), g = 0..3: afterwards this thread holds i, f, g, o of unit ju at
+        // rows 16 part + 4k + g, k = 0..3
+        float vi[4], vf[4], vg[4], vo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x0 = a[4 * k], x1 = a[4 * k + 1], x2 = a[4 * k + 2], x3 = a[4 * k + 3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, g0 ? x0 : x1, 8);
+          const float r1 = __shfl_xor_sync(0xffffffffu, g0 ? x2 : x3, 8);
+          const float p0lo = g0 ? r0 : x0, p0hi = g0 ? x1 : r0;     // (lo gate, hi gate) of row g0
+          const float p1lo = g0 ? r1 : x2, p1hi = g0 ? x3 : r1;     // ... of row 2 + g0
+          const float s0 = __shfl_xor_sync(0xffffffffu, g1 ? p0lo : p1lo, 16);
+          const float s1 = __shfl_xor_sync(0xffffffffu, g1 ? p0hi : p1hi, 16);
+          vi[k] = g1 ? s0 : p0lo; vf[k] = g1 ? s1 : p0hi;
+          vg[k] = g1 ? p1lo : s0; vo[k] = g1 ? p1hi : s1;
+        }
+        if (ps == 0) {
+          mbar_wait(&cin_full[buf], upar);        // c_{t-1} tile landed
+          WL_STAMP(12);
+        }
+        // all loads, then the math, then all stores: the staging pointers alias as far as the compiler can tell
+        float cv[4], hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cv[k] = lds_f32(cin_a + part * 2048 + k * 512 + cx[k & 1]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cv[k] = vf[k] * cv[k] + vi[k] * vg[k];
+          hv[k] = vo[k] * tanh_approx(cv[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          sts_f32(sb_a + kWlOffC + part * 2048 + k * 512 + cx[k & 1], cv[k]);
+          sts_f32(sb_a + kWlOffC + part * 2048 + (k + 1) * 512 + cx[(k + 1) & 1], cv[k + 1]);
+          const uint32_t h16 = pack_f16x2(hv[k], hv[k + 1]);
+          sts_u16(sb_a + kWlOffH16 + part * 1024 + k * 256 + hx, (uint16_t)(h16 & 0xffffu));
+          sts_u16(sb_a + kWlOffH16 + part * 1024 + (k + 1) * 256 + hx, (uint16_t)(h16 >> 16));
+          if (p.training) {
+            const uint32_t hb = pack_bf16x2(hv[k], hv[k + 1]);
+            sts_u16(sb_a + kWlOffHbf + part * 1024 + k * 256 + hx, (uint16_t)(hb & 0xffffu));
+            sts_u16(sb_a + kWlOffHbf + part * 1024 + (k + 1) * 256 + hx, (uint16_t)(hb >> 16));
+          }
+        }
+        if (p.h_last && l == p.L - 1 && t == T - 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int m = j * kWlTile + part * 16 + 4 * k + g;
+            if (m < p.B) p.h_last[(size_t)m * H + n * 32 + unit] = hv[k];
+          }
+        }
+      }
+      if (!is_R) {
+        mbar_wait(&gin_taken[buf], upar ^ 1);     // the signal warp has consumed this barrier's previous phase
+        mbar_arrive(&gin_done[buf]);              // the signal warp publishes the tile
+        WL_STAMP(13);
+        continue;
+      }
+      if (p.ablate & 2) {
+        mbar_wait(&stg_free[buf], upar ^ 1);
+        mbar_wait(&cin_full[buf], upar);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&stg_full[buf]);
+      WL_STAMP(13);
+    }
+  } else if (warp == kWlWarpStore && !is_R) {
+    // ------------------------------------------------------------------ signal warp (P): publish gin tiles
+    if (lane == 0) {
+      for (long long it = 0; it < total; ++it) {
+        mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1));
+        mbar_arrive(&gin_taken[it & 1]);
+        fence_acq_rel_gpu();                      // cumulative over the 512 threads' stores ordered by the mbarrier
+        st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + (it % nt), (unsigned)(it / nt + 1));
+      }
+    }
+  } else if (warp == kWlWarpStore && is_R) {
+    // ------------------------------------------------------------------ store + signal warp (R only)
+    if (elect_one()) {
+      long long it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          mbar_wait(&stg_full[buf], upar);
+          long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
+          WL_STAMP(14);
+          const uint8_t* sb = stg + buf * kWlStgBytes;
+          const int row0 = j * kWlTile;
+          tma_store_3d(&ly.t_h16_st, sb + kWlOffH16, n * 32, row0, t + 1);
+          tma_store_3d(&ly.t_c, sb + kWlOffC, n * 32, row0, p.training ? t + 1 : ((t + 1) & 1));
+          if (p.training) {
+            tma_store_3d(&ly.t_hbf_st, sb + kWlOffHbf, n * 32, row0, t + 1);
+            tma_store_3d(&ly.t_gates, sb + kWlOffG, n * 128, row0, t);
+            tma_store_3d(&ly.t_gates, sb + kWlOffG + 8192, n * 128 + 64, row0, t);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // complete (performed at L2, the point of coherence; implies the staging buffer has been read).  No
+          // generic-proxy write of this thread precedes the counter, so a relaxed increment publishes the tile: a
+          // release, a proxy fence and __threadfence cost ~1000 cycles EACH per tile here.
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          mbar_arrive(&stg_free[buf]);
+          red_relaxed_add(p.hcnt + l * nt + j, 1u);
+          WL_STAMP(15);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWlWarpMma) tmem_dealloc<512>(tmem);
+}
+
+template <int H>
+static int launch_wlstm_fwd(WlstmParams& p, cudaStream_t s) {
+  auto kern = wlstm_fwd_kernel<H>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWlSmem);
+    if (e != cudaSuccess) { set_error("wlstm: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
+    configured = true;
+  }
+  void* args[] = {&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3(2 * p.L * (H / 32)), dim3(kWlThreads), args, kWlSmem, s);
+  if (e != cudaSuccess) { set_error("wlstm: cooperative launch", e); return SVB_ERR_CUDA; }
+  return SVB_OK;
+}
