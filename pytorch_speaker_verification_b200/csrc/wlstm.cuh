@@ -96,10 +96,11 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // arrival traps instead of hanging the GPU.
 // NO acquire / proxy fence follows on purpose.  Everything that is read after the flag bypasses L1 (TMA loads and
 // ld.global.cg go to L2, the point of coherence) and is issued only after the flag value has come back (the poller
-// arrives on an mbarrier that the consumers wait on), and the writers completed their data at L2 before raising the
-// flag (TMA stores: cp.async.bulk.wait_group; gin: fence.acq_rel.gpu in the signal warp).  fence.acq_rel.gpu and
-// fence.proxy.async cost ~1000 cycles EACH here and made this loop (3 fences per tile) the limiter of the whole
-// kernel: 2.2 us per tile with all math, loads and stores switched off.
+// arrives on an mbarrier that the consumers wait on), and the writers release their data at gpu scope before raising
+// the flag (TMA stores: cp.async.bulk.wait_group + red.release; gin: fence.acq_rel.gpu in every writing thread).
+// fence.acq_rel.gpu and fence.proxy.async cost ~1000 cycles EACH here and made this loop (3 fences per tile) the
+// limiter of the whole kernel: 2.2 us per tile with all math, loads and stores switched off.  The poisoned-workspace
+// stress test guards this protocol.
 __device__ __forceinline__ void wait_two_counters(const unsigned* a, unsigned ta, const unsigned* b, unsigned tb) {
   long long t0 = 0;
   while (true) {
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
 
+  const long long t_cta0 = clock64();
   if (warp == kWlWarpPoll && lane == 0) {
     // ------------------------------------------------------------------ dependency poller (runs ahead of the rest)
     // A satisfied poll still costs an L2 round trip (~1000 clk); here it overlaps the previous tiles' work.
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         for (int j = 0; j < nt; ++j, ++it) {
           const int d = (int)(it % kWlDeps);
           mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1));
-          if (is_R) {
+          if (p.ablate & 8) {
+          } else if (is_R) {
             wait_two_counters(t > 0 ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * t),
                               p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
           } else {
@@ -326,7 +329,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // ------------------------------------------------------------------ epilogue: thread = gate column (TMEM lane)
     // Two groups of 8 warps work on alternate tiles (group = accumulator buffer), so that one group's MUFU-bound
     // activation phase overlaps the other's shuffle / shared-memory phases and the ~170-cycle mbarrier waits.
-    // Within a group two warps share a TMEM lane quarter; each takes two 16-row parts of the 64-row tile.
+    // Within a group two warps share a TMEM lane quarter; each takes two 16-row parts of the 64-row tile.  The
+    // accumulator is drained into registers first so that the MMA of tile it+2 starts while this epilogue runs.
     const int grp = warp >> 3;                 // tiles it = grp, grp + 2, ... (accumulator / staging buffer = grp)
     const int q = warp & 3;                    // TMEM lane quarter
     const int sub = (warp >> 2) & 1;           // parts sub and sub + 2: rows [16 part, 16 part + 16)
@@ -343,76 +347,82 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // shared-memory addresses of this thread's slots, swizzle terms folded in (row & 7 is known at compile time below)
     const uint32_t sb_a = smem_u32(stg) + buf * kWlStgBytes;
     const int cb2 = (q & 1) * 32 + lane;                               // column within the 64-column gate box
-    uint32_t gbase[8];                                                 // gate stash: row i -> gbase[i & 7] + i * 128
-#pragma unroll
-    for (int m = 0; m < 8; ++m) gbase[m] = sb_a + kWlOffG + (q >> 1) * 8192 + (((cb2 >> 3) ^ m) << 4) + (cb2 & 7) * 2;
+    // gate stash: row i -> (gbase0 ^ ((i & 7) << 4)) + i * 128  (bits 4..6 of gbase0 hold only the 16-byte unit index)
+    const uint32_t gbase0 = sb_a + kWlOffG + (q >> 1) * 8192 + ((cb2 >> 3) << 4) + (cb2 & 7) * 2 + sub * 2048;
     uint32_t cx[2];                                                    // c tile: row 4k + g -> cx[k & 1] + k * 512
 #pragma unroll
-    for (int e = 0; e < 2; ++e) cx[e] = g * 128 + ((((unit >> 2) ^ ((e << 2) | g))) << 4) + (unit & 3) * 4;
+    for (int e = 0; e < 2; ++e) cx[e] = sub * 2048 + g * 128 + ((((unit >> 2) ^ ((e << 2) | g))) << 4) + (unit & 3) * 4;
     const uint32_t cin_a = smem_u32(cin) + buf * kWlCinBytes;
-    const uint32_t hx = g * 64 + unit * 2;                             // h tiles: row 4k + g -> hx + k * 256
+    const uint32_t hx = sub * 1024 + g * 64 + unit * 2;                // h tiles: row 4k + g -> hx + k * 256
     for (long long it = grp; it < total; it += 2) {
       const int t = (int)(it / nt), j = (int)(it % nt);
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
-      float4* gfrag = reinterpret_cast<float4*>(ly.gin) + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 2048 + col;
-      float4 gv[2][4];
+      float4* gfrag = reinterpret_cast<float4*>(ly.gin) + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 2048 +
+                      (size_t)sub * 512 + col;      // + ps * 1024 + k * 128 float4
+      float4 gv[4];
       long long* tr = (trace_cta && t == T / 2 && (warp & 7) == 0 && lane == 0) ? trace_cta + j * 16 : nullptr;
       WL_STAMP(7);
       if (is_R) {
         const int d = (int)(it % kWlDeps);
         mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));     // gin of (t, j) is published
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) gv[ps][k] = __ldcg(gfrag + ((sub + 2 * ps) * 4 + k) * 128);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dep_free[d]);
+        for (int k = 0; k < 4; ++k) gv[k] = __ldcg(gfrag + k * 128);
       }
       WL_STAMP(8);
       mbar_wait(&acc_full[buf], upar);
       tc_fence_after();
       WL_STAMP(9);
-#pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int part = sub + 2 * ps;
-        float acc[16];
-        tmem_ld16(tmem + lane_base + kWlAccCol + buf * kWlTile + part * 16, acc);
-        tmem_ld_wait();
-        if (ps == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        if (!is_R) {
-          // gin = W_ih x + bias, in fragment order: float4 (rows 4r..4r+3) of column `col` at [r][col]
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            gfrag[(part * 4 + k) * 128] = make_float4(acc[4 * k] + bias, acc[4 * k + 1] + bias, acc[4 * k + 2] + bias,
-                                                      acc[4 * k + 3] + bias);
-          continue;
-        }
-        if (p.ablate & 2) continue;
-        // ---- activations of this thread's gate column for 16 rows
-        float a[16];
+      float a0[16], a1[16];
+      tmem_ld16(tmem + lane_base + kWlAccCol + buf * kWlTile + sub * 16, a0);
+      tmem_ld16(tmem + lane_base + kWlAccCol + buf * kWlTile + sub * 16 + 32, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (!is_R) {
+        // gin = W_ih x + bias, in fragment order: float4 (rows 4r..4r+3) of column `col` at [r][col]
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          a[4 * k + 0] = fmaf(ca, tanh_approx((acc[4 * k + 0] + gv[ps][k].x) * cs), cb);
-          a[4 * k + 1] = fmaf(ca, tanh_approx((acc[4 * k + 1] + gv[ps][k].y) * cs), cb);
-          a[4 * k + 2] = fmaf(ca, tanh_approx((acc[4 * k + 2] + gv[ps][k].z) * cs), cb);
-          a[4 * k + 3] = fmaf(ca, tanh_approx((acc[4 * k + 3] + gv[ps][k].w) * cs), cb);
+          gfrag[k * 128] = make_float4(a0[4 * k] + bias, a0[4 * k + 1] + bias, a0[4 * k + 2] + bias, a0[4 * k + 3] + bias);
+          gfrag[1024 + k * 128] = make_float4(a1[4 * k] + bias, a1[4 * k + 1] + bias, a1[4 * k + 2] + bias, a1[4 * k + 3] + bias);
+        }
+        // every thread completes its own stores at gpu scope (the 512 fences overlap; ONE fence in the signal warp
+        // after the barrier waited ~3500 cycles per tile for the whole CTA's 32 KB and was the limiter of P)
+        fence_acq_rel_gpu();
+        mbar_wait(&gin_taken[buf], upar ^ 1);     // the signal warp has consumed this barrier's previous phase
+        mbar_arrive(&gin_done[buf]);              // the signal warp publishes the tile
+        WL_STAMP(13);
+        continue;
+      }
+#pragma unroll
+      for (int ps = 0; ps < 2; ++ps) {
+        float (&a)[16] = ps == 0 ? a0 : a1;
+        // ---- activations of this thread's gate column for 16 rows
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[4 * k + 0] = fmaf(ca, tanh_approx((a[4 * k + 0] + gv[k].x) * cs), cb);
+          a[4 * k + 1] = fmaf(ca, tanh_approx((a[4 * k + 1] + gv[k].y) * cs), cb);
+          a[4 * k + 2] = fmaf(ca, tanh_approx((a[4 * k + 2] + gv[k].z) * cs), cb);
+          a[4 * k + 3] = fmaf(ca, tanh_approx((a[4 * k + 3] + gv[k].w) * cs), cb);
         }
         if (ps == 0) {
+          // gin of the second part: in flight while the first part is processed
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gv[k] = __ldcg(gfrag + 1024 + k * 128);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dep_free[(int)(it % kWlDeps)]);
           WL_STAMP(10);
           mbar_wait(&stg_free[buf], upar ^ 1);    // staging buffer drained by the store warp
           WL_STAMP(11);
         }
+        if (p.ablate & 2) continue;
         if (p.training) {
           // gate stash [row][packed col] bf16: two boxes of 64 columns, 128B-swizzled rows
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const uint32_t pk = pack_bf16x2(a[i], a[i + 1]);
-            sts_u16(gbase[i & 7] + part * 2048 + i * 128, (uint16_t)(pk & 0xffffu));
-            sts_u16(gbase[(i + 1) & 7] + part * 2048 + (i + 1) * 128, (uint16_t)(pk >> 16));
+            sts_u16((gbase0 ^ ((i & 7) << 4)) + ps * 4096 + i * 128, (uint16_t)(pk & 0xffffu));
+            sts_u16((gbase0 ^ (((i + 1) & 7) << 4)) + ps * 4096 + (i + 1) * 128, (uint16_t)(pk >> 16));
           }
         }
         // 4 x 4 transposes across the lanes (g, ju), g = 0..3: afterwards this thread holds i, f, g, o of unit ju at
@@ -434,10 +444,10 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           mbar_wait(&cin_full[buf], upar);        // c_{t-1} tile landed
           WL_STAMP(12);
         }
-        // all loads, then the math, then all stores: the staging pointers alias as far as the compiler can tell
+        // all loads, then the math, then all stores
         float cv[4], hv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cv[k] = lds_f32(cin_a + part * 2048 + k * 512 + cx[k & 1]);
+        for (int k = 0; k < 4; ++k) cv[k] = lds_f32(cin_a + ps * 4096 + k * 512 + cx[k & 1]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           cv[k] = vf[k] * cv[k] + vi[k] * vg[k];
@@ -445,35 +455,26 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         }
 #pragma unroll
         for (int k = 0; k < 4; k += 2) {
-          sts_f32(sb_a + kWlOffC + part * 2048 + k * 512 + cx[k & 1], cv[k]);
-          sts_f32(sb_a + kWlOffC + part * 2048 + (k + 1) * 512 + cx[(k + 1) & 1], cv[k + 1]);
+          sts_f32(sb_a + kWlOffC + ps * 4096 + k * 512 + cx[k & 1], cv[k]);
+          sts_f32(sb_a + kWlOffC + ps * 4096 + (k + 1) * 512 + cx[(k + 1) & 1], cv[k + 1]);
           const uint32_t h16 = pack_f16x2(hv[k], hv[k + 1]);
-          sts_u16(sb_a + kWlOffH16 + part * 1024 + k * 256 + hx, (uint16_t)(h16 & 0xffffu));
-          sts_u16(sb_a + kWlOffH16 + part * 1024 + (k + 1) * 256 + hx, (uint16_t)(h16 >> 16));
+          sts_u16(sb_a + kWlOffH16 + ps * 2048 + k * 256 + hx, (uint16_t)(h16 & 0xffffu));
+          sts_u16(sb_a + kWlOffH16 + ps * 2048 + (k + 1) * 256 + hx, (uint16_t)(h16 >> 16));
           if (p.training) {
             const uint32_t hb = pack_bf16x2(hv[k], hv[k + 1]);
-            sts_u16(sb_a + kWlOffHbf + part * 1024 + k * 256 + hx, (uint16_t)(hb & 0xffffu));
-            sts_u16(sb_a + kWlOffHbf + part * 1024 + (k + 1) * 256 + hx, (uint16_t)(hb >> 16));
+            sts_u16(sb_a + kWlOffHbf + ps * 2048 + k * 256 + hx, (uint16_t)(hb & 0xffffu));
+            sts_u16(sb_a + kWlOffHbf + ps * 2048 + (k + 1) * 256 + hx, (uint16_t)(hb >> 16));
           }
         }
         if (p.h_last && l == p.L - 1 && t == T - 1) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int m = j * kWlTile + part * 16 + 4 * k + g;
+            const int m = j * kWlTile + (sub + 2 * ps) * 16 + 4 * k + g;
             if (m < p.B) p.h_last[(size_t)m * H + n * 32 + unit] = hv[k];
           }
         }
       }
-      if (!is_R) {
-        mbar_wait(&gin_taken[buf], upar ^ 1);     // the signal warp has consumed this barrier's previous phase
-        mbar_arrive(&gin_done[buf]);              // the signal warp publishes the tile
-        WL_STAMP(13);
-        continue;
-      }
-      if (p.ablate & 2) {
-        mbar_wait(&stg_free[buf], upar ^ 1);
-        mbar_wait(&cin_full[buf], upar);
-      }
+      if (p.ablate & 2) mbar_wait(&cin_full[buf], upar);
       fence_proxy_async_smem();
       mbar_arrive(&stg_full[buf]);
       WL_STAMP(13);
@@ -484,7 +485,6 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       for (long long it = 0; it < total; ++it) {
         mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1));
         mbar_arrive(&gin_taken[it & 1]);
-        fence_acq_rel_gpu();                      // cumulative over the 512 threads' stores ordered by the mbarrier
         st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + (it % nt), (unsigned)(it / nt + 1));
       }
     }
@@ -509,12 +509,14 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
             tma_store_3d(&ly.t_gates, sb + kWlOffG + 8192, n * 128 + 64, row0, t);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          // complete (performed at L2, the point of coherence; implies the staging buffer has been read).  No
-          // generic-proxy write of this thread precedes the counter, so a relaxed increment publishes the tile: a
-          // release, a proxy fence and __threadfence cost ~1000 cycles EACH per tile here.
+          // complete (implies the staging buffer has been read), then a RELEASE increment publishes the tile.  The
+          // release is required: with a relaxed increment other CTAs' TMA loads read stale rows of the tile (found
+          // with a NaN-poisoned workspace, tests/test_gpu_parity.py::test_persistent_kernel_no_stale_reads).  One
+          // fence is enough and costs nothing at the current period; proxy fence + __threadfence + release together
+          // cost ~3000 cycles per tile and made this warp the limiter.
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           mbar_arrive(&stg_free[buf]);
-          red_relaxed_add(p.hcnt + l * nt + j, 1u);
+          red_release_add(p.hcnt + l * nt + j, 1u);
           WL_STAMP(15);
         }
       }
@@ -523,6 +525,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == kWlWarpMma) tmem_dealloc<512>(tmem);
+  if (p.trace && threadIdx.x == 0) p.trace[4 * nt * 16 + cta] = clock64() - t_cta0;
 }
 
 template <int H>

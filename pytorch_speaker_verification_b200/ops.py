@@ -11,6 +11,9 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
+import os
+
+_POISON = os.environ.get("SVB_POISON_WORKSPACE", "0") == "1"
 _i64 = ctypes.c_int64
 _sz = ctypes.c_size_t
 
@@ -31,8 +34,15 @@ def _stage(t, dtype=None):
     return t.contiguous()
 
 
+def set_poison_workspace(on):
+    """Debug: NaN-fill every forward workspace, so that a kernel reading a slot before it is written shows up."""
+    global _POISON
+    _POISON = bool(on)
+
+
 def set_persistent(on):
-    """Select the recurrent forward kernel: True (default) persistent cooperative kernel, False per-frame launches."""
+    """Select the LSTM forward path: True (default) persistent wavefront kernel (csrc/wlstm.cuh), False per-frame
+    launches (csrc/lstm.cu)."""
     check(_lib.lib().svb_set_persistent(int(bool(on))), "svb_set_persistent")
 
 
@@ -84,6 +94,8 @@ class EmbedderFn(torch.autograd.Function):
             check(_lib.lib().svb_embedder_sizes(B, T, I, H, L, P, int(training), None, ctypes.byref(wbytes)),
                   "svb_embedder_sizes")
             ws = torch.empty(wbytes.value, dtype=torch.uint8, device=xg.device)
+            if _POISON:          # debug: NaN-fill the workspace so that any read of a not-yet-written slot shows
+                ws.fill_(255)
             emb = torch.empty(B, P, dtype=torch.float32, device=xg.device)
             check(_lib.lib().svb_embedder_forward(ptr(xg), 0 if xg.dtype == torch.float32 else 1, ptr(packed),
                                                   ptr(dev_params[4 * L]), ptr(dev_params[4 * L + 1]), ptr(emb), ptr(ws),

@@ -14,7 +14,7 @@ net = svb.SpeechEmbedder().cuda()
 B, T = 640, 160
 x = torch.tensor(I.logmel(B, T, seed=1234)).cuda()
 nt = (B + 63) // 64
-buf = torch.zeros(4 * nt * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4 * nt * 16 + 256, dtype=torch.int64, device="cuda")
 for i in range(3):
     if i == 2: L.svb_set_trace(ctypes.c_void_p(buf.data_ptr()))
     if training:
@@ -23,7 +23,8 @@ for i in range(3):
         with torch.no_grad(): e = net(x)
     torch.cuda.synchronize()
 L.svb_set_trace(None)
-t = buf.cpu().numpy().reshape(4, nt, 16).astype(np.float64)
+dur = buf[4 * nt * 16:].cpu().numpy()
+t = buf[:4 * nt * 16].cpu().numpy().reshape(4, nt, 16).astype(np.float64)
 names = ["prod_start", "prod_flags_ok", "prod_issued", "mma_start", "mma_acc_free", "mma_first_full", "mma_last_full",
          "epi_start", "epi_gin_ok", "epi_acc_full", "epi_act_done", "epi_stg_free", "epi_cin_ok", "epi_done",
          "st_begin", "st_done"]
@@ -42,3 +43,7 @@ for j in range(nt):
 print("MMA detail R(1,0): (before_wait, after_wait) x 6 groups, issued_all | producer issue time of groups 0,1,2")
 for j in range(nt):
     print(f"  j={j:2d} " + " ".join(f"{(v - t0) if v > 0 else -1:7.0f}" for v in t[3, j, :16]))
+
+print("per-CTA kernel-loop cycles per tile (mean over the 24 slices): ",
+      {f"R{l}": round(float(dur[l*24:(l+1)*24].mean()) / (T * nt)) for l in range(3)},
+      {f"P{l}": round(float(dur[72+l*24:72+(l+1)*24].mean()) / (T * nt)) for l in range(3)})

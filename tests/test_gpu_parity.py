@@ -241,12 +241,14 @@ def test_embedder_forward_matches_reference(svb, net):
 
 
 def test_persistent_and_per_frame_kernels_agree(svb, net):
-    """The persistent recurrent kernel (W_hh resident in smem, h staged through TMEM, flag barriers per batch
-    tile) and the per-frame kernels compute the same embeddings and the same BPTT stash."""
+    """The persistent wavefront kernel (weights stationary in tensor memory, all layers in one launch, flag-ordered
+    tiles; MUFU.TANH activations, single-term fp16 layer-0 projection) and the per-frame kernels (3-term layer-0
+    projection, ex2/rcp activations) both meet the 1e-3 embedding bar and agree with each other well inside it;
+    their BPTT stashes give the same gradients within the gradient tolerance."""
     from pytorch_speaker_verification_b200 import ops
     g = load("embedder_c1.npz")
     x = torch.tensor(I.logmel(20, 180, seed=1234)).cuda()
-    xb = torch.tensor(I.logmel(300, 50, seed=77)).cuda()          # 3 batch tiles, ragged last tile
+    xb = torch.tensor(I.logmel(300, 50, seed=77)).cuda()          # 5 batch tiles, ragged last tile
     try:
         out = {}
         for mode in (True, False):
@@ -256,12 +258,44 @@ def test_persistent_and_per_frame_kernels_agree(svb, net):
             net.zero_grad()
             e = net(xb[:140])
             e.square().sum().mul(0.5).add(e.sum()).backward()
-            out[mode] += (net.LSTM_stack.weight_hh_l0.grad.clone(), net.LSTM_stack.weight_ih_l2.grad.clone())
+            out[mode] += (net.LSTM_stack.weight_hh_l0.grad.clone(), net.LSTM_stack.weight_ih_l2.grad.clone(),
+                          net.LSTM_stack.bias_ih_l1.grad.clone(), net.LSTM_stack.weight_ih_l0.grad.clone())
     finally:
-        ops.set_persistent(False)
-    assert emb_err(out[True][0].cpu().numpy(), g["emb"]) < 1e-3
-    for a, b in zip(out[True], out[False]):
-        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (a - b).abs().max()
+        ops.set_persistent(True)
+    for mode in (True, False):
+        assert emb_err(out[mode][0].cpu().numpy(), g["emb"]) < 1e-3, (mode, emb_err(out[mode][0].cpu().numpy(), g["emb"]))
+    for a, b in zip(out[True][:2], out[False][:2]):
+        assert emb_err(a.cpu().numpy(), b.cpu().numpy()) < 5e-4
+    for a, b in zip(out[True][2:], out[False][2:]):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-2, rel_l2(a.cpu().numpy(), b.cpu().numpy())
+    print("persistent vs golden:", emb_err(out[True][0].cpu().numpy(), g["emb"]),
+          "per-frame vs golden:", emb_err(out[False][0].cpu().numpy(), g["emb"]))
+
+
+def test_persistent_kernel_no_stale_reads(svb, net):
+    """Flag protocol of the persistent kernel under a NaN-poisoned workspace: a tile read before its producer's
+    stores are visible shows up as NaN (this is how the missing release on the h-tile counter was found).  Small
+    batches keep producer and consumer closest in time; results must also be run-to-run identical and independent of
+    the batch composition."""
+    from pytorch_speaker_verification_b200 import ops
+    try:
+        ops.set_poison_workspace(True)
+        for (B, T) in ((35, 24), (50, 40), (100, 40), (200, 30), (640, 20)):
+            x = torch.tensor(I.logmel(B, T, seed=B)).cuda()
+            with torch.no_grad():
+                ref = net(x)
+                assert not torch.isnan(ref).any()
+                for _ in range(25):
+                    assert torch.equal(net(x), ref)
+                assert torch.equal(net(x[:B // 3]), ref[:B // 3])
+            net.zero_grad()
+            net(x).square().sum().backward()
+            g1 = net.LSTM_stack.weight_hh_l1.grad.clone()
+            net.zero_grad()
+            net(x).square().sum().backward()
+            assert torch.isfinite(g1).all() and torch.equal(g1, net.LSTM_stack.weight_hh_l1.grad)
+    finally:
+        ops.set_poison_workspace(False)
 
 
 def test_embedder_saturated_weights(svb):
