@@ -83,9 +83,9 @@ class ClockSampler:
 
 
 def launches_per_step(world):
-    fwd = 1 + NLAYER * (1 + T_FR) + 1                 # prep, per layer input GEMM + T fused step kernels, projection
+    fwd = 1 + 1 + 1                                    # prep, persistent wavefront LSTM kernel (all layers, all frames), projection
     loss = 1                                           # fused GE2E (cooperative)
-    bwd = 1 + 4 + NLAYER * (T_FR + 2 + 2) + (NLAYER - 1)   # scale3, projection bwd, per layer BPTT + 2 wgrad + 2 bias, dX
+    bwd = 1 + 4 + 1 + NLAYER * (2 + 2)                 # scale3, projection bwd, persistent BPTT (all layers, dX fused), per layer 2 wgrad + 2 bias
     pack = NLAYER                                      # bf16 shadow refresh after the optimizer step
     return fwd + loss + bwd + pack
 
@@ -357,7 +357,15 @@ def main():
         # roofline of the dominant kernel class
         flops_step = 2.0 * B * 4 * HID * HID               # one recurrent frame: (B x H) . (H x 4H), fwd == bwd
         dom = max(("recurrent_fwd", "recurrent_bwd", "input_gemm", "weight_grads"), key=lambda k: phases[k])
-        if dom in ("recurrent_fwd", "recurrent_bwd"):
+        if dom == "recurrent_fwd" and args.recurrent_terms == 1:
+            launches = 1                                  # one persistent launch: input projections + recurrence, all layers
+            flops_launch = 23838720.0 * T_FR * B
+            kern = "wlstm_fwd_kernel (persistent wavefront LSTM forward)"
+        elif dom == "recurrent_bwd" and args.recurrent_terms == 1:
+            launches = 1                                  # one persistent launch: recurrent + dX products, all layers
+            flops_launch = 2.0 * B * T_FR * 4 * HID * HID * (2 * NLAYER - 1)
+            kern = "wbptt_kernel (persistent wavefront BPTT)"
+        elif dom in ("recurrent_fwd", "recurrent_bwd"):
             launches = NLAYER * T_FR
             flops_launch = flops_step * args.recurrent_terms if dom == "recurrent_fwd" else flops_step
             kern = "tc_gemm_kernel<EpiLstmFwd>" if dom == "recurrent_fwd" else "tc_gemm_kernel<EpiLstmBwd>"
@@ -379,8 +387,8 @@ def main():
             "config": {"workload": "GE2E train step, 64 speakers x 10 utts x 160 frames x 40 mel per GPU "
                                    "(BASELINE configs[1]; global batch = 64 x n_gpus speakers, configs[2] at 8)",
                        "model": "3-layer LSTM 40->768, Linear 768->256, L2 norm; GE2E w=10 b=-5; reference init seed 0",
-                       "precision": f"input projection split-bf16 x3, recurrent bf16 x{args.recurrent_terms}, "
-                                    "fp32 accumulate/gates/loss",
+                       "precision": "forward GEMMs fp16 x fp16 (single term), MUFU.TANH gates; BPTT GEMMs bf16; "
+                                    "fp32 accumulate/cell state/loss",
                        "parallelism": f"dp{world} by speaker group" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (untimed)",
                        "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
@@ -392,13 +400,15 @@ def main():
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
                          # (profiles/r1_ncu_full_summary.txt); the frame kernels' writes stay in the 126 MB L2
-                         "traffic": {"recurrent_fwd": 15556352, "recurrent_bwd": 18506752,
-                                     "input_gemm": 325408256 + 1203885000}.get(dom),
+                         "traffic": {"recurrent_bwd": 18506752}.get(dom),
                          "peak_source": f"{pk_src} (sustained bf16)",
                          "avg_launch_us": avg_ms * 1e3, "launches_per_step": launches,
                          # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)
                          "whole_step_frac": 11443765248.0 * B / 1e12 / (ms_value * 1e-3) / peak},
             "phases_ms": phases,
+            "forward_kernel": {"name": "wlstm_fwd_kernel", "ms": phases["recurrent_fwd"],
+                               "tflops": 23838720.0 * T_FR * B / (phases["recurrent_fwd"] * 1e-3) / 1e12,
+                               "frac_of_sustained_bf16_peak": 23838720.0 * T_FR * B / (phases["recurrent_fwd"] * 1e-3) / 1e12 / peak},
             "secondary": extra,
             "loss": loss_val,
         }

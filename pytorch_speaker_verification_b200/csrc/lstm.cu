@@ -97,6 +97,10 @@ struct Work {
   __nv_bfloat16* gates[8];          // [T+1, B, 4H] (training)
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
   float *dh_above, *dc, *dh_last, *dy;  // backward: [T,B,H], [B,H], [B,H], [B,P]
+  float* dcl[8];                    // persistent BPTT: running dL/dc per layer [B,H]
+  float* xring[8];                  // persistent BPTT: dX ring of layer l >= 1, [3][nt][H/32][64 x 32] fp32
+  unsigned *dcnt, *xcnt;            // persistent BPTT progress counters [L][nt], [L][H/32][nt]
+  size_t bcnt_bytes;
   float* colsum_part;               // [chunks, 4H]
   float* gin_ring[8];               // persistent kernel: [kWlGinRing][nt][H/32][64 x 128] fp32 per layer
   unsigned *hcnt, *gcnt;            // persistent kernel: [L][nt] and [L][H/32][nt] progress counters
@@ -137,6 +141,14 @@ static Work layout_work(char* base, const Dims& d, int training) {
     w.dh_last = (float*)take(B * H * 4);
     w.dy = (float*)take(B * d.P * 4);
     w.colsum_part = (float*)take(((T * B + kColsumRows - 1) / kColsumRows) * 4 * H * 4);
+    const size_t nt = (B + 63) / 64, NS = H / 32;
+    for (int l = 0; l < d.L; ++l) {
+      w.dcl[l] = (float*)take(B * H * 4);
+      w.xring[l] = l > 0 ? (float*)take((size_t)3 * nt * NS * 2048 * 4) : nullptr;
+    }
+    w.bcnt_bytes = al256((size_t)d.L * nt * 4) + al256((size_t)d.L * NS * nt * 4);
+    w.dcnt = (unsigned*)take(w.bcnt_bytes);
+    w.xcnt = w.dcnt + al256((size_t)d.L * nt * 4) / 4;
   }
   w.bytes = off;
   return w;
@@ -367,6 +379,8 @@ struct EpiLstmBwd {
 
 #include "wlstm.cuh"
 static_assert(kWlGinRing == 3, "layout_work sizes the gin ring for 3 frames");
+#include "wbptt.cuh"
+static_assert(kWbXRing == 3, "layout_work sizes the dX ring for 3 frames");
 
 // ------------------------------------------------------------------------------------------ projection + L2 norm
 // y[b,:] = W h_last[b,:] + bias; emb = y/|y|   (speech_embedder_net.py:31-32; fp32; 8 batch rows per CTA)
@@ -521,9 +535,11 @@ struct Profiler {
 };
 static Profiler g_prof;
 static int g_persistent = 1;   // persistent wavefront forward kernel (wlstm.cuh) when the shape allows
+static int g_persistent_bwd = 1;   // persistent wavefront BPTT kernel (wbptt.cuh) when the shape allows
 static int g_fwd_pair = 0;     // forward frame: CTA pairs share the W_hh slice (measured slower: cluster barriers outweigh the ingest saving)
 static int g_bwd_splitk = 1;   // BPTT frame: 4-CTA cluster split-K with DSMEM partial exchange
 static int g_ablate = 0;      // debug: persistent kernel ablation mask (timing experiments only)
+static unsigned long long* g_trace_bwd = nullptr;   // debug: stamps of the persistent BPTT kernel
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
 static void prof_mark(int phase, cudaStream_t s) {   // phase >= 0: start of a phase; -1: end marker
   if (!g_prof.on || g_prof.n >= 256) return;
@@ -555,9 +571,11 @@ using namespace svb;
 
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
+extern "C" int svb_set_persistent_bwd(int on) { g_persistent_bwd = on != 0; return SVB_OK; }
 extern "C" int svb_set_fwd_pair(int on) { g_fwd_pair = on != 0; return SVB_OK; }
 extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
 extern "C" int svb_set_ablate(int mask) { g_ablate = mask; return SVB_OK; }
+extern "C" int svb_set_trace_bwd(unsigned long long* buf) { g_trace_bwd = buf; return SVB_OK; }
 extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
 extern "C" int svb_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; return SVB_OK; }
 // Sums the elapsed ms per phase since the last enable/read; the caller must have synchronised the stream.
@@ -743,6 +761,32 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   colsum_f32_kernel<<<(P + 127) / 128, 128, 0, s>>>(w.dy, grads[4 * L + 1], B, P);
   sgemm_small(w.dy, proj_w, w.dh_last, B, H, P, 0, 0, s);               // dh_last[B,H] = dy W_proj
   SVB_CUDA("projection backward");
+  bool use_wbptt = false;
+  if (g_persistent_bwd && H == 768 && L <= 3) {
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    use_wbptt = 4 * (2 * L - 1) * (H / 128) + 16 <= num_sms;    // clusters of 4 strand up to 16 SMs
+  }
+  if (use_wbptt) {
+    // ---- BPTT of the whole stack (recurrent products, dX products, gate backward) in one persistent kernel
+    prof_mark(PH_REC_BWD, s);
+    const int nt = (B + kWbTile - 1) / kWbTile;
+    WbParams bp;
+    memset(&bp, 0, sizeof(bp));
+    for (int l = 0; l < L; ++l) {
+      WbLayer& ly = bp.layer[l];
+      SVB_TRY(make_tmap(&ly.t_dg, w.gates[l], 2, 4 * H, B, T + 1, 4 * H, (uint64_t)B * 4 * H, 64, kWbTile, 3));
+      SVB_TRY(make_tmap(&ly.t_c, w.c[l], 4, H, B, T + 1, H, BH, 32, kWbTile, 3));
+      SVB_TRY(make_tmap(&ly.t_dc, w.dcl[l], 4, H, B, 1, H, BH, 32, kWbTile, 3));
+      ly.whhT = pw.l[l].whhT; ly.wihT = pw.l[l].wihT; ly.xring = w.xring[l];
+      cudaMemsetAsync(w.dcl[l], 0, BH * 4, s);
+    }
+    bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last;
+    bp.trace = reinterpret_cast<long long*>(g_trace_bwd);
+    bp.B = B; bp.T = T; bp.L = L; bp.H = H; bp.nt = nt;
+    cudaMemsetAsync(w.dcnt, 0, w.bcnt_bytes, s);
+    SVB_TRY(launch_wbptt<768>(bp, s));
+  }
   for (int l = L - 1; l >= 0; --l) {
     const LayerW& lw = pw.l[l];
     prof_mark(PH_REC_BWD, s);
@@ -761,7 +805,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     SVB_TRY(make_tmap(&ep.t_dc, w.dc, 4, H, B, 1, H, BH, 32, 128, 3));
     if (l == L - 1) SVB_TRY(make_tmap(&ep.t_dha, w.dh_last, 4, H, B, 1, H, BH, 32, 128, 3));
     else SVB_TRY(make_tmap(&ep.t_dha, w.dh_above, 4, H, B, T, H, BH, 32, 128, 3));
-    for (int t = T - 1; t >= 0; --t) {
+    for (int t = T - 1; t >= 0 && !use_wbptt; --t) {
       ops.za[0] = t + 1;
       ops.trace = (g_trace && l == 1 && t == T / 2) ? g_trace + 4096 : nullptr;
       ep.t = t;
@@ -813,7 +857,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     }
     // ---- gradient w.r.t. the layer input = dh_above of the layer below: dX[T*B, H] = dG W_ih
     prof_mark(PH_DX, s);
-    if (l > 0) {
+    if (l > 0 && !use_wbptt) {
       GemmOperands g;
       memset(&g, 0, sizeof(g));
       g.nterms = 1; g.M = TB; g.N = H; g.K = 4 * H;

@@ -1,0 +1,541 @@
+// Persistent wavefront BPTT kernel: the time-reversed counterpart of wlstm.cuh (included by lstm.cu, namespace svb).
+//
+// Replaces, for the whole stack at once, the per-frame BPTT launches and the batched dX GEMMs behind
+// train_speech_embedder.py:62 (autograd through nn.LSTM):
+//     dh^l_t = dG^l_{t+1} W_hh^l + dG^{l+1}_t W_ih^{l+1}         (top layer: + dL/dh_last at t = T-1)
+//     dG^l_t = gate backward(dh^l_t, gates_t, c_t, c_{t-1}, running dL/dc)
+// The reductions run over K = 4H = 3072 gate columns, the outputs over H = 768 units, so a [128 units x 768 K]
+// weight slice fills the 192 KB of tensor memory that a CTA can devote to the stationary A operand, and a product
+// needs (H/128) x 4 = 24 CTAs: clusters of 4 CTAs share one 128-unit tile and split K four ways.
+//
+//   R(l, u, s)  recurrent product of layer l, unit tile u, K slice s: streams dG^l_{t+1}[64-row tile, K slice] (bf16,
+//               TMA -> smem ring) against W_hh^T[tile, slice] in TMEM; the accumulator D[unit (lane), row (column)]
+//               is a PARTIAL sum.  CTA s of the cluster owns units [32 s, 32 s + 32) of the tile: every CTA pushes
+//               the other three quarters of its partial into the owners' shared memory (st.shared::cluster,
+//               lane-contiguous 16-byte stores), owners add the three they receive, the dX tile from X(l+1, u, s)
+//               and run the gate backward for their 32 units: dG_t overwrites the gate stash in place (TMA store).
+//   X(l, u, s)  input-gradient product of layer l >= 1 (dX^{l-1}_t = dG^l_t W_ih^l), same cluster scheme; the owner
+//               writes its reduced [32 units x 64 rows] fp32 tile to a small L2-resident ring in fragment order for
+//               R(l-1, u, s), which owns the same units.
+//
+// Ordering by release/acquire counters as in wlstm.cuh:
+//   dcnt[l][j]      += 1 by every R(l, ., .) after its dG stores of (t, j) completed: dG^l_t[tile j] complete at
+//                      NS * (T - t)
+//   xcnt[l][ns][j]   = T - t by X(l, u, s) (ns = 4 u + s) once dX of (t, j) is written
+// 30 clusters of 4 = 120 CTAs, all co-resident (cooperative launch).
+#pragma once
+
+constexpr int kWbTile = 64;
+constexpr int kWbKb = 12;              // 64-wide K blocks per CTA (K slice of 768)
+constexpr int kWbKbPerStage = 3;       // 12 MMAs per barrier wait
+constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages)
+constexpr int kWbStageBytes = kWbKbPerStage * kWbTile * 128;
+constexpr int kWbXRing = 3;
+constexpr int kWbDeps = 4;
+constexpr int kWbEpiWarps = 16;
+constexpr int kWbThreads = 32 * kWbEpiWarps + 128;
+constexpr int kWbWarpTma = kWbEpiWarps, kWbWarpMma = kWbEpiWarps + 1, kWbWarpStore = kWbEpiWarps + 2,
+              kWbWarpPoll = kWbEpiWarps + 3;   // lane 0: dependency poller, lane 1: epilogue-input loader
+constexpr int kWbAccCol = 384;
+// epilogue tiles (in place): gates / dG 2 x 8 KB boxes, c_t, c_{t-1}, dc
+constexpr int kWbOffG = 0, kWbOffCt = 16384, kWbOffCp = 24576, kWbOffDc = 32768, kWbStgBytes = 40960;
+constexpr int kWbRecvBytes = 3 * 8192;  // three peers' partial quarters: [slot][part 4][k 4][lane 32] float4
+constexpr int kWbDhBytes = 8192;        // reduced dh tile [64 rows][32 units] fp32
+constexpr int kWbSmem = kWbStages * kWbStageBytes + 2 * kWbStgBytes + 2 * kWbRecvBytes + 2 * kWbDhBytes + 1024 + 1024;
+static_assert(kWbSmem <= 227 * 1024, "shared memory budget of the BPTT kernel");
+
+struct __align__(64) WbLayer {
+  CUtensorMap t_dg;        // bf16 gates / dG [T+1][B][4H], box {64, 64} SW128: B operand, gate tile load + store
+  CUtensorMap t_c;         // fp32 c [T+1][B][H], box {32, 64} SW128
+  CUtensorMap t_dc;        // fp32 running dL/dc [1][B][H], box {32, 64} SW128, load + store
+  const __nv_bfloat16* whhT;   // [H][4H]
+  const __nv_bfloat16* wihT;   // [H][4H] (layers >= 1)
+  float* xring;            // dX produced by X(l): [kWbXRing][nt][H/32][64 x 32] fp32, fragment order (layers >= 1)
+};
+struct __align__(64) WbParams {
+  WbLayer layer[3];
+  unsigned* dcnt;          // [L][nt]
+  unsigned* xcnt;          // [L][H/32][nt]
+  const float* dh_last;    // [B][H] dL/dh of the top layer's last frame
+  long long* trace;
+  int B, T, L, H, nt;
+};
+
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta) {
+  const uint32_t addr = map_to_cta(smem_u32(local_bar), cta);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// relaxed variant: signals "I have consumed your data" (the loads it orders have already returned their values)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* local_bar, uint32_t cta) {
+  const uint32_t addr = map_to_cta(smem_u32(local_bar), cta);
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("svb: cluster mbarrier wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_constant__ WbParams p) {
+  constexpr int NS = H / 32;                 // 32-unit slices per layer (= R CTAs per layer)
+  constexpr int NU = H / 128;                // 128-unit tiles (= clusters per product)
+  static_assert(H % 128 == 0 && 4 * H == 4 * kWbKb * 64, "the K slices must be 768 wide");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* stg = ring + kWbStages * kWbStageBytes;
+  uint8_t* recv = stg + 2 * kWbStgBytes;
+  uint8_t* dhb = recv + 2 * kWbRecvBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dhb + 2 * kWbDhBytes);
+  uint64_t* empty = full + kWbStages;
+  uint64_t* acc_full = empty + kWbStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2] 16 warps
+  uint64_t* in_full = acc_empty + 2;           // [2] epilogue input tiles landed (tx)
+  uint64_t* stg_full = in_full + 2;            // [2] 512 threads: outputs staged
+  uint64_t* stg_free = stg_full + 2;           // [2] store thread: staging buffer reusable
+  uint64_t* recv_full = stg_free + 2;          // [2] 12 remote warps: partial quarters of the three peers landed
+  uint64_t* peer_free = recv_full + 2;         // [2] 12 remote warps: my three receivers consumed tile it-2
+  uint64_t* dep_ready = peer_free + 2;         // [kWbDeps]
+  uint64_t* dep_free = dep_ready + kWbDeps;    // [kWbDeps]
+  uint64_t* x_done = dep_free + kWbDeps;       // [2] X: owner threads wrote the dX tile
+  uint64_t* x_taken = x_done + 2;              // [2]
+  uint64_t* dh_full = x_taken + 2;             // [2] 64 owner threads: reduced dh tile written
+  uint64_t* dh_free = dh_full + 2;             // [2] 256 math threads: dh tile consumed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dh_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cl = blockIdx.x >> 2;
+  const int s = (int)cluster_ctarank();        // K slice and owned unit quarter
+  const bool is_R = cl < p.L * NU;
+  const int l = is_R ? cl / NU : 1 + (cl - p.L * NU) / NU;
+  const int u = is_R ? cl % NU : (cl - p.L * NU) % NU;
+  const int ns = 4 * u + s;                    // 32-unit slice index within the layer
+  const WbLayer& ly = p.layer[l];
+  const int nt = p.nt, T = p.T;
+  const long long total = (long long)T * nt;
+  const bool has_x = is_R && l + 1 < p.L;      // dX from the layer above arrives through its ring
+  // debug trace: R(1, 0, 0) rows [0, nt), X(1, 0, 0) rows [nt, 2 nt): 16 clock64 stamps per tile of frame T/2
+  long long* const trace_cta = (p.trace && l == 1 && u == 0 && s == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+  const long long t_cta0 = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWbStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);               // the eight exchange warps
+      mbar_init(&in_full[b], 1);
+      mbar_init(&stg_full[b], 256);              // the eight math warps
+      mbar_init(&stg_free[b], 1);
+      mbar_init(&recv_full[b], 6);               // 3 senders x 2 warps
+      mbar_init(&peer_free[b], 6);               // 3 receivers x 2 owner warps
+      mbar_init(&x_done[b], 64);
+      mbar_init(&x_taken[b], 1);
+      mbar_init(&dh_full[b], 64);
+      mbar_init(&dh_free[b], 256);
+    }
+    for (int d = 0; d < kWbDeps; ++d) {
+      mbar_init(&dep_ready[d], 1);
+      mbar_init(&dep_free[d], is_R ? 2 + 2 : 1);     // producer (+ input loader + the two owner warps of R)
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&ly.t_dg);
+  }
+  if (warp == kWbWarpMma) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  cluster_sync_all();                          // every CTA's barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  // ---- weights -> tensor memory (once): lane r = unit 128 u + r, K slice [768 s, 768 s + 768) of the 4H gate columns
+  if (warp < 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const __nv_bfloat16* wrow = (is_R ? ly.whhT : ly.wihT) + (size_t)(u * 128 + r) * (4 * H) + s * (kWbKb * 64);
+    for (int kb = 0; kb < kWbKb; ++kb) {
+      uint32_t v[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(wrow + kb * 64 + i * 8));
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+      }
+      tmem_st32(tmem + (uint32_t(q * 32) << 16) + kb * 32, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kWbWarpPoll && lane == 0) {
+    // ------------------------------------------------------------------ dependency poller
+    long long it = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      for (int j = 0; j < nt; ++j, ++it) {
+        const int d = (int)(it % kWbDeps);
+        mbar_wait(&dep_free[d], (uint32_t)(((it / kWbDeps) & 1) ^ 1));
+        if (is_R) {
+          wait_two_counters(t < T - 1 ? p.dcnt + l * nt + j : nullptr, (unsigned)(NS * (T - 1 - t)),
+                            has_x ? p.xcnt + ((size_t)(l + 1) * NS + ns) * nt + j : nullptr, (unsigned)(T - t));
+        } else {
+          wait_two_counters(p.dcnt + l * nt + j, (unsigned)(NS * (T - t)),
+                            T - t > kWbXRing ? p.dcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (T - t - kWbXRing)));
+        }
+        mbar_arrive(&dep_ready[d]);
+      }
+    }
+  } else if (warp == kWbWarpPoll && lane == 1) {
+    // ------------------------------------------------------------------ epilogue-input loader (R only)
+    if (is_R) {
+      long long it = 0;
+      for (int t = T - 1; t >= 0; --t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          const int d = (int)(it % kWbDeps);
+          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));   // our own dc store of frame t+1 is complete
+          mbar_arrive(&dep_free[d]);
+          mbar_wait(&stg_free[buf], upar ^ 1);                       // the stores of tile it-2 have left the buffer
+          uint8_t* sb = stg + buf * kWbStgBytes;
+          mbar_expect_tx(&in_full[buf], kWbStgBytes);
+          tma_load_3d(sb + kWbOffG, &ly.t_dg, &in_full[buf], ns * 128, j * kWbTile, t);
+          tma_load_3d(sb + kWbOffG + 8192, &ly.t_dg, &in_full[buf], ns * 128 + 64, j * kWbTile, t);
+          tma_load_3d(sb + kWbOffCt, &ly.t_c, &in_full[buf], ns * 32, j * kWbTile, t + 1);
+          tma_load_3d(sb + kWbOffCp, &ly.t_c, &in_full[buf], ns * 32, j * kWbTile, t);
+          tma_load_3d(sb + kWbOffDc, &ly.t_dc, &in_full[buf], ns * 32, j * kWbTile, 0);
+        }
+      }
+    }
+  } else if (warp == kWbWarpTma) {
+    // ------------------------------------------------------------------ TMA producer (B operand = dG rows)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (int t = T - 1; t >= 0; --t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int d = (int)(it % kWbDeps);
+          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));
+          mbar_arrive(&dep_free[d]);
+          const int slab = is_R ? t + 1 : t;
+          for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], kWbStageBytes);
+#pragma unroll
+            for (int k = 0; k < kWbKbPerStage; ++k)
+              tma_load_3d(ring + stage * kWbStageBytes + k * (kWbTile * 128), &ly.t_dg, &full[stage],
+                          s * (kWbKb * 64) + (gi * kWbKbPerStage + k) * 64, j * kWbTile, slab);
+            if (++stage == kWbStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == kWbWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (A = W^T slice in TMEM, bf16)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kWbTile, 0, 0);
+    const uint64_t desc0 = umma_desc_kmajor_sw128(smem_u32(ring));
+    const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
+    int stage = 0;
+    uint32_t phase = 0;
+    const long long my_total = elect_one() ? total : 0;
+    for (long long it = 0; it < my_total; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t upar = (uint32_t)((it >> 1) & 1);
+      long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;
+      WL_STAMP(0);
+      mbar_wait(&acc_empty[buf], upar ^ 1);
+      tc_fence_after();
+      WL_STAMP(1);
+      for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (gi == 0) WL_STAMP(2);
+        if (gi == kWbKb / kWbKbPerStage - 1) WL_STAMP(3);
+        const uint32_t lo = desc_lo0 + stage * (kWbStageBytes >> 4);
+        const uint32_t a0 = tmem + gi * kWbKbPerStage * 32;
+        const uint32_t dacc = tmem + kWbAccCol + buf * kWbTile;
+#pragma unroll
+        for (int q = 0; q < 4 * kWbKbPerStage; ++q)
+          umma_f16_ts_lohi(dacc, a0 + q * 8, lo + (q >> 2) * ((kWbTile * 128) >> 4) + (q & 3) * 2, desc_hi, idesc,
+                           q == 0 ? (gi != 0 ? 1u : 0u) : 1u);
+        umma_commit(&empty[stage]);
+        if (gi == kWbKb / kWbKbPerStage - 1) umma_commit(&acc_full[buf]);
+        if (++stage == kWbStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ exchange warps: TMEM -> split-K reduction
+    // Two warps per TMEM lane quarter (= unit quarter of the tile), 32 rows each in two passes of 16.  The DSMEM
+    // exchange (24 KB out + 24 KB in per tile at ~17 B/clk) is the longest stage of the tile; it runs here,
+    // decoupled from the gate backward of the previous tile (math warps) and from the MMAs of the next.
+    const int q = warp & 3;
+    const int half = warp >> 2;                // rows [32 half, 32 half + 32)
+    const bool owner = q == s;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const uint32_t recv_a = smem_u32(recv), dh_a = smem_u32(dhb);
+    const bool use_x = owner && has_x;
+    long long it = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      for (int j = 0; j < nt; ++j, ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t upar = (uint32_t)((it >> 1) & 1);
+        const int d = (int)(it % kWbDeps);
+        long long* tr = (trace_cta && t == T / 2 && lane == 0 && warp < 2) ? trace_cta + j * 16 : nullptr;
+        if (warp == 0) WL_STAMP(4);
+        const float4* xf = nullptr;
+        float4 xv[4];
+        if (owner && is_R) {
+          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));
+          if (use_x) {
+            // dX tile of the layer above, in flight while the partial sums arrive
+            xf = reinterpret_cast<const float4*>(p.layer[l + 1].xring) + ((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512 +
+                 (half * 8) * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xv[k] = __ldcg(xf + k * 32);
+          }
+        }
+        if (warp == 0) WL_STAMP(5);
+        mbar_wait(&acc_full[buf], upar);
+        tc_fence_after();
+        if (warp == 0) WL_STAMP(6);
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int rg0 = half * 8 + ps * 4;   // first 4-row group of this pass
+          float v[16];
+          tmem_ld16(tmem + lane_base + kWbAccCol + buf * kWbTile + rg0 * 4, v);
+          tmem_ld_wait();
+          if (ps == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          if (!owner) {
+            // push this quarter of the partial sum to its owner (CTA q): slot (s - q - 1) mod 4 of its receive buffer
+            if (ps == 0) {
+              if (warp == 1) WL_STAMP(12);
+              mbar_wait_cluster(&peer_free[buf], upar ^ 1);
+              if (warp == 1) WL_STAMP(13);
+            }
+            const uint32_t dst = map_to_cta(recv_a + buf * kWbRecvBytes + ((s - q - 1) & 3) * 8192 + rg0 * 512 + lane * 16,
+                                            (uint32_t)q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st_cluster_f4(dst + k * 512, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            if (ps == 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(&recv_full[buf], (uint32_t)q);
+              if (warp == 1) WL_STAMP(14);
+            }
+            continue;
+          }
+          if (ps == 0) {
+            mbar_wait_cluster(&recv_full[buf], upar);
+            if (warp == 0) WL_STAMP(7);
+          }
+#pragma unroll
+          for (int sl = 0; sl < 3; ++sl)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 r = lds_f4(recv_a + buf * kWbRecvBytes + sl * 8192 + (rg0 + k) * 512 + lane * 16);
+              v[4 * k] += r.x; v[4 * k + 1] += r.y; v[4 * k + 2] += r.z; v[4 * k + 3] += r.w;
+            }
+          if (ps == 1) {
+            __syncwarp();
+            // three lanes signal the three senders in parallel (a remote arrive is a ~1000-cycle round trip)
+            if (lane < 3) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
+          }
+          if (!is_R) {
+            // dX tile -> ring, fragment order [row group][lane] float4 = rows 4 rg .. 4 rg + 3 of unit `lane`
+            float4* xo = reinterpret_cast<float4*>(ly.xring) + ((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512 + rg0 * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xo[k * 32] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            if (ps == 1) {
+              fence_acq_rel_gpu();
+              mbar_wait(&x_taken[buf], upar ^ 1);
+              mbar_arrive(&x_done[buf]);
+            }
+            continue;
+          }
+          if (use_x) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[4 * k] += xv[k].x; v[4 * k + 1] += xv[k].y; v[4 * k + 2] += xv[k].z; v[4 * k + 3] += xv[k].w; }
+            if (ps == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) xv[k] = __ldcg(xf + (4 + k) * 32);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&dep_free[d]);
+            }
+          } else {
+            if (ps == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&dep_free[d]); }
+            if (l == p.L - 1 && t == T - 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int m = j * kWbTile + rg0 * 4 + i;
+                if (m < p.B) v[i] += __ldg(p.dh_last + (size_t)m * H + ns * 32 + lane);
+              }
+            }
+          }
+          // reduced dh tile [row][unit] fp32 for the gate backward (math warps)
+          if (ps == 0) mbar_wait(&dh_free[buf], upar ^ 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sts_f32(dh_a + buf * kWbDhBytes + (rg0 * 4 + i) * 128 + lane * 4, v[i]);
+          if (ps == 1) mbar_arrive(&dh_full[buf]);
+        }
+        if (warp == 0) WL_STAMP(8);
+      }
+    }
+  } else if (warp < kWbEpiWarps) {
+    // ------------------------------------------------------------------ math warps (R): gate backward, in place
+    if (is_R) {
+      const uint32_t dh_a = smem_u32(dhb), stg_a = smem_u32(stg);
+      const int mt = threadIdx.x - 256;          // 0..255 -> (row, 8 consecutive units as two groups of 4)
+      const int row = mt >> 2;
+      long long it = 0;
+      for (int t = T - 1; t >= 0; --t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          long long* tr = (trace_cta && t == T / 2 && threadIdx.x == 256) ? trace_cta + j * 16 : nullptr;
+          WL_STAMP(9);
+          mbar_wait(&dh_full[buf], upar);
+          mbar_wait(&in_full[buf], upar);
+          WL_STAMP(10);
+          const uint32_t sb = stg_a + buf * kWbStgBytes;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int ug = (mt & 3) * 2 + hh;      // units 4 ug .. 4 ug + 3 of the CTA's 32
+            const int G = ug >> 1;                 // group of 8 units
+            const uint32_t g_off = (G >> 1) * 8192 + row * 128 + 8 * (ug & 1);
+            const uint32_t u_off = row * 128 + ((ug ^ (row & 7)) << 4);
+            const float4 dh4 = lds_f4(dh_a + buf * kWbDhBytes + row * 128 + ug * 16);
+            const float4 ct4 = lds_f4(sb + kWbOffCt + u_off), cp4 = lds_f4(sb + kWbOffCp + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
+            uint32_t gaddr[4];
+            uint2 gq[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              gaddr[g] = sb + kWbOffG + g_off + (((4 * (G & 1) + g) ^ (row & 7)) << 4);
+              gq[g] = lds_u2(gaddr[g]);
+            }
+            const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
+            const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcs[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+            float gi[4], gf[4], gg[4], go[4], di[4], df[4], dg[4], dO[4], dcn[4];
+            gi[0] = bf16_lo_of(gq[0].x); gi[1] = bf16_hi_of(gq[0].x); gi[2] = bf16_lo_of(gq[0].y); gi[3] = bf16_hi_of(gq[0].y);
+            gf[0] = bf16_lo_of(gq[1].x); gf[1] = bf16_hi_of(gq[1].x); gf[2] = bf16_lo_of(gq[1].y); gf[3] = bf16_hi_of(gq[1].y);
+            gg[0] = bf16_lo_of(gq[2].x); gg[1] = bf16_hi_of(gq[2].x); gg[2] = bf16_lo_of(gq[2].y); gg[3] = bf16_hi_of(gq[2].y);
+            go[0] = bf16_lo_of(gq[3].x); go[1] = bf16_hi_of(gq[3].x); go[2] = bf16_lo_of(gq[3].y); go[3] = bf16_hi_of(gq[3].y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float tc = tanh_approx(ct[i]);
+              const float dc = dh[i] * go[i] * (1.f - tc * tc) + dcs[i];
+              dO[i] = dh[i] * tc * go[i] * (1.f - go[i]);
+              di[i] = dc * gg[i] * gi[i] * (1.f - gi[i]);
+              df[i] = dc * cp[i] * gf[i] * (1.f - gf[i]);
+              dg[i] = dc * gi[i] * (1.f - gg[i] * gg[i]);
+              dcn[i] = dc * gf[i];
+            }
+            sts_u2(gaddr[0], make_uint2(pack_bf16x2(di[0], di[1]), pack_bf16x2(di[2], di[3])));
+            sts_u2(gaddr[1], make_uint2(pack_bf16x2(df[0], df[1]), pack_bf16x2(df[2], df[3])));
+            sts_u2(gaddr[2], make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3])));
+            sts_u2(gaddr[3], make_uint2(pack_bf16x2(dO[0], dO[1]), pack_bf16x2(dO[2], dO[3])));
+            sts_f4(sb + kWbOffDc + u_off, make_float4(dcn[0], dcn[1], dcn[2], dcn[3]));
+          }
+          mbar_arrive(&dh_free[buf]);
+          fence_proxy_async_smem();
+          mbar_arrive(&stg_full[buf]);
+          WL_STAMP(11);
+        }
+      }
+    }
+  } else if (warp == kWbWarpStore && !is_R) {
+    // ------------------------------------------------------------------ signal warp (X): publish dX tiles
+    if (lane == 0) {
+      for (long long it = 0; it < total; ++it) {
+        mbar_wait(&x_done[it & 1], (uint32_t)((it >> 1) & 1));
+        mbar_arrive(&x_taken[it & 1]);
+        st_relaxed(p.xcnt + ((size_t)l * NS + ns) * nt + (it % nt), (unsigned)(it / nt + 1));
+      }
+    }
+  } else if (warp == kWbWarpStore && is_R) {
+    // ------------------------------------------------------------------ store + signal warp (R)
+    if (elect_one()) {
+      long long it = 0;
+      for (int t = T - 1; t >= 0; --t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          const int buf = (int)(it & 1);
+          const uint32_t upar = (uint32_t)((it >> 1) & 1);
+          mbar_wait(&stg_full[buf], upar);
+          const uint8_t* sb = stg + buf * kWbStgBytes;
+          tma_store_3d(&ly.t_dg, sb + kWbOffG, ns * 128, j * kWbTile, t);
+          tma_store_3d(&ly.t_dg, sb + kWbOffG + 8192, ns * 128 + 64, j * kWbTile, t);
+          tma_store_3d(&ly.t_dc, sb + kWbOffDc, ns * 32, j * kWbTile, 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          mbar_arrive(&stg_free[buf]);
+          red_release_add(p.dcnt + l * nt + j, 1u);      // release: see wlstm.cuh
+          if (trace_cta && t == T / 2) trace_cta[j * 16 + 15] = clock64();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                          // no CTA leaves while a peer may still push into or signal it
+  if (warp == kWbWarpMma) tmem_dealloc<512>(tmem);
+  if (p.trace && threadIdx.x == 0) p.trace[2 * nt * 16 + blockIdx.x] = clock64() - t_cta0;
+}
+
+template <int H>
+static int launch_wbptt(WbParams& p, cudaStream_t s) {
+  auto kern = wbptt_kernel<H>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWbSmem);
+    if (e != cudaSuccess) { set_error("wbptt: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * (2 * p.L - 1) * (H / 128));
+  cfg.blockDim = dim3(kWbThreads);
+  cfg.dynamicSmemBytes = kWbSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) { set_error("wbptt: cooperative cluster launch", e); return SVB_ERR_CUDA; }
+  return SVB_OK;
+}

@@ -46,6 +46,11 @@ def set_persistent(on):
     check(_lib.lib().svb_set_persistent(int(bool(on))), "svb_set_persistent")
 
 
+def set_persistent_bwd(on):
+    """Select the BPTT path: True (default) persistent wavefront kernel (csrc/wbptt.cuh), False per-frame launches."""
+    check(_lib.lib().svb_set_persistent_bwd(int(bool(on))), "svb_set_persistent_bwd")
+
+
 def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 

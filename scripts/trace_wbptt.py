@@ -1,0 +1,32 @@
+"""Dev: clock64 stamps of R(1,0,0) and X(1,0,0) of the persistent BPTT kernel at frame T/2 (cycles, per tile)."""
+import ctypes, sys
+import numpy as np, torch
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import _inputs as I
+import pytorch_speaker_verification_b200 as svb
+from pytorch_speaker_verification_b200 import _lib
+L = _lib.lib()
+torch.manual_seed(0)
+net = svb.SpeechEmbedder().cuda()
+B, T = 640, 160
+x = torch.tensor(I.logmel(B, T, seed=1234)).cuda()
+nt = (B + 63) // 64
+buf = torch.zeros(2 * nt * 16 + 256, dtype=torch.int64, device="cuda")
+for i in range(3):
+    if i == 2: L.svb_set_trace_bwd(ctypes.c_void_p(buf.data_ptr()))
+    net.zero_grad()
+    e = net(x); e.square().sum().backward()
+    torch.cuda.synchronize()
+L.svb_set_trace_bwd(None)
+dur = buf[2 * nt * 16:].cpu().numpy()
+t = buf[:2 * nt * 16].cpu().numpy().reshape(2, nt, 16).astype(np.float64)
+names = ["mma_start", "mma_accfree", "mma_full0", "mma_fullL", "epi_start", "epi_dep_ok", "epi_accfull", "own_recv_ok",
+         "own_reduced", "bar_done", "in_full_ok", "epi_done", "snd_start", "snd_peer_ok", "snd_sent", "store_done"]
+for r, tag in enumerate(("R(1,0,0)", "X(1,0,0)")):
+    t0 = t[r][t[r] > 0].min()
+    print(tag)
+    print("      " + " ".join(f"{n[:11]:>11s}" for n in names))
+    for j in range(nt):
+        print(f"  j={j:2d} " + " ".join(f"{(v - t0) if v > 0 else -1:11.0f}" for v in t[r, j]))
+print("per-CTA cycles per tile:", {f"R{l}": round(float(dur[l*24:(l+1)*24].mean()) / (T * nt)) for l in range(3)},
+      {f"X{l}": round(float(dur[72+(l-1)*24:72+l*24].mean()) / (T * nt)) for l in (1, 2)})

@@ -272,6 +272,28 @@ def test_persistent_and_per_frame_kernels_agree(svb, net):
           "per-frame vs golden:", emb_err(out[False][0].cpu().numpy(), g["emb"]))
 
 
+def test_persistent_bptt_matches_per_frame_bptt(svb, net):
+    """The persistent wavefront BPTT kernel (split-K over 4-CTA clusters with a DSMEM reduction, dX products fused
+    in) and the per-frame BPTT kernels + batched dX GEMMs consume the same stash and agree on every parameter
+    gradient far inside the gradient tolerance."""
+    from pytorch_speaker_verification_b200 import ops
+    out = {}
+    try:
+        for (B, T) in ((20, 6), (140, 50), (300, 21)):
+            x = torch.tensor(I.logmel(B, T, seed=B + T)).cuda()
+            for mode in (True, False):
+                ops.set_persistent_bwd(mode)
+                net.zero_grad()
+                e = net(x)
+                e.square().sum().mul(0.5).add(e.sum()).backward()
+                out[mode] = {k: p.grad.clone() for k, p in net.named_parameters()}
+            for k in out[True]:
+                assert torch.isfinite(out[True][k]).all(), k
+                assert rel_l2(out[True][k].cpu().numpy(), out[False][k].cpu().numpy()) < 2e-3, (B, T, k)
+    finally:
+        ops.set_persistent_bwd(True)
+
+
 def test_persistent_kernel_no_stale_reads(svb, net):
     """Flag protocol of the persistent kernel under a NaN-poisoned workspace: a tile read before its producer's
     stores are visible shows up as NaN (this is how the missing release on the h-tile counter was found).  Small
