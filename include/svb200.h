@@ -45,12 +45,13 @@ int svb_embedder_sizes(int B, int T, int I, int H, int L, int P, int training, s
                        size_t* workspace_bytes);
 
 /* Re-pack the fp32 master parameters of nn.LSTM (state_dict order: weight_ih, weight_hh, bias_ih, bias_hh per layer;
- * HOST array of 4L DEVICE pointers; speech_embedder_net.py:19-24) into gate-interleaved bf16 hi/lo shadows. */
+ * HOST array of 4L DEVICE pointers; speech_embedder_net.py:19-24) into gate-interleaved shadows: fp16 (+ fp16
+ * residual) for the forward GEMMs, bf16 transposes for the BPTT GEMMs. */
 int svb_embedder_pack_weights(const float* const* params, void* packed, int I, int H, int L, void* stream);
 
 /* SpeechEmbedder.forward (speech_embedder_net.py:27-33). x: (B,T,I) batch-first, x_dtype 0=float32 1=float64
- * (":28 x.float()"); emb: (B,P) float32 unit rows.  rec_terms 1..3 = number of split-bf16 terms of the recurrent
- * GEMM (1: h_hi W_hi; 2: + h_hi W_lo; 3: + h_lo W_hi).  With training != 0 the workspace afterwards holds the stash that
+ * (":28 x.float()"); emb: (B,P) float32 unit rows.  rec_terms = number of weight terms of the forward GEMMs
+ * (1: h16 W16, persistent kernel; 2 or 3: + h16 W16_residual, per-frame kernels).  With training != 0 the workspace afterwards holds the stash that
  * svb_embedder_backward consumes. */
 int svb_embedder_forward(const void* x, int x_dtype, const void* packed, const float* proj_w, const float* proj_b,
                          float* emb, void* workspace, int B, int T, int I, int H, int L, int P, int training,
@@ -61,10 +62,20 @@ int svb_embedder_forward(const void* x, int x_dtype, const void* packed, const f
 int svb_embedder_backward(const float* demb, const void* packed, const float* proj_w, float* const* grads,
                           void* workspace, int B, int T, int I, int H, int L, int P, void* stream);
 
-/* Recurrent forward kernel selection: 0 (default) = one fused GEMM+cell launch per frame (TMA-staged epilogue);
- * 1 = experimental persistent cooperative kernel (W_hh resident in shared memory, h staged through tensor memory,
- * per-batch-tile frame counters) when H is 256/512/768 and rec_terms == 1. */
+/* LSTM forward path: 1 (default) = persistent wavefront kernel (csrc/wlstm.cuh: all layers and frames in one
+ * cooperative launch, W_hh / W_ih slices stationary in tensor memory, fp16 operands, MUFU.TANH gates, tiles ordered by
+ * release counters) when H is 256/512/768, L <= 3 and rec_terms == 1; 0 = batched input projection + one fused
+ * GEMM+cell launch per frame (any H % 128 == 0, split terms). */
 int svb_set_persistent(int on);
+/* BPTT path: 1 (default) = persistent wavefront kernel (csrc/wbptt.cuh: recurrent and dX products of all layers in
+ * one cooperative cluster launch, split-K over 4-CTA clusters with a DSMEM reduction) when H == 768 and L <= 3;
+ * 0 = one fused GEMM + gate-backward launch per frame and batched dX GEMMs. */
+int svb_set_persistent_bwd(int on);
+/* Debug hooks of the persistent kernels (timing experiments only): ablation mask (results become garbage) and
+ * clock64 trace buffers (device pointers, or NULL). */
+int svb_set_ablate(int mask);
+int svb_set_trace(unsigned long long* device_buffer);
+int svb_set_trace_bwd(unsigned long long* device_buffer);
 
 /* Optional phase timing (CUDA events around the phases of forward/backward; none inside the per-frame loops).
  * Phases: 0 prep, 1 input GEMM, 2 recurrent fwd, 3 projection, 4 projection bwd, 5 recurrent bwd, 6 weight grads,
