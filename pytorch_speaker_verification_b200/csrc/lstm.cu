@@ -779,6 +779,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       SVB_TRY(make_tmap(&ly.t_c, w.c[l], 4, H, B, T + 1, H, BH, 32, kWbTile, 3));
       SVB_TRY(make_tmap(&ly.t_dc, w.dcl[l], 4, H, B, 1, H, BH, 32, kWbTile, 3));
       ly.whhT = pw.l[l].whhT; ly.wihT = pw.l[l].wihT; ly.xring = w.xring[l];
+      ly.gbias_ih = grads[4 * l + 2]; ly.gbias_hh = grads[4 * l + 3];
       cudaMemsetAsync(w.dcl[l], 0, BH * 4, s);
     }
     bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last;
@@ -848,7 +849,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       if (e != cudaSuccess) { set_error("dW_ih", e); return SVB_ERR_CUDA; }
     }
     prof_mark(PH_BIAS, s);
-    {
+    if (!use_wbptt) {      // (the persistent BPTT kernel accumulates the column sums of dG itself)
       const int chunks = (TB + kColsumRows - 1) / kColsumRows;
       dim3 grid((4 * H / 8 + 255) / 256, chunks);
       colsum_bf16_kernel<<<grid, 256, 0, s>>>(w.gates[l], w.colsum_part, TB, 4 * H);

@@ -51,6 +51,8 @@ struct __align__(64) WbLayer {
   const __nv_bfloat16* whhT;   // [H][4H]
   const __nv_bfloat16* wihT;   // [H][4H] (layers >= 1)
   float* xring;            // dX produced by X(l): [kWbXRing][nt][H/32][64 x 32] fp32, fragment order (layers >= 1)
+  float* gbias_ih;         // bias gradients of the layer (reference row order), written at the end of the kernel
+  float* gbias_hh;         // b_ih and b_hh enter the pre-activation as a sum: identical gradients
 };
 struct __align__(64) WbParams {
   WbLayer layer[3];
@@ -421,6 +423,9 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       const uint32_t dh_a = smem_u32(dhb), stg_a = smem_u32(stg);
       const int mt = threadIdx.x - 256;          // 0..255 -> (row, 8 consecutive units as two groups of 4)
       const int row = mt >> 2;
+      float bsum[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bsum[i] = 0.f;
       long long it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
@@ -464,6 +469,13 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
               dg[i] = dc * gi[i] * (1.f - gg[i] * gg[i]);
               dcn[i] = dc * gf[i];
             }
+            // bias gradients: per-thread partial column sums of dG over all tiles and frames (reduced over the 64 rows
+            // once, at the end of the kernel)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bsum[hh * 16 + i] += di[i]; bsum[hh * 16 + 4 + i] += df[i];
+              bsum[hh * 16 + 8 + i] += dg[i]; bsum[hh * 16 + 12 + i] += dO[i];
+            }
             sts_u2(gaddr[0], make_uint2(pack_bf16x2(di[0], di[1]), pack_bf16x2(di[2], di[3])));
             sts_u2(gaddr[1], make_uint2(pack_bf16x2(df[0], df[1]), pack_bf16x2(df[2], df[3])));
             sts_u2(gaddr[2], make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3])));
@@ -475,6 +487,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           mbar_arrive(&stg_full[buf]);
           WL_STAMP(11);
         }
+      }
+      // partial sums -> shared memory [row][packed column] (the operand ring is idle by now: the last MMA of this CTA
+      // completed before the last accumulator was handed to the exchange warps)
+      float* bsc = reinterpret_cast<float*>(ring);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int ug = (mt & 3) * 2 + hh;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bsc[row * 128 + 32 * (ug >> 1) + 8 * g + 4 * (ug & 1) + i] = bsum[hh * 16 + g * 4 + i];
       }
     }
   } else if (warp == kWbWarpStore && !is_R) {
@@ -509,6 +532,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     }
   }
   tc_fence_before();
+  __syncthreads();
+  if (is_R && threadIdx.x < 128 && ly.gbias_ih) {
+    // this CTA owns packed gate columns [128 ns, 128 ns + 128) for all rows and frames: finish the bias gradients
+    const float* bsc = reinterpret_cast<const float*>(ring);
+    float sum = 0.f;
+    for (int r64 = 0; r64 < 64; ++r64) sum += bsc[r64 * 128 + threadIdx.x];
+    const int pc = ns * 128 + threadIdx.x;                           // packed column
+    const int r = ((pc & 31) >> 3) * H + (pc >> 5) * 8 + (pc & 7);   // reference row (gate-major i|f|g|o)
+    ly.gbias_ih[r] = sum;
+    ly.gbias_hh[r] = sum;
+  }
   cluster_sync_all();                          // no CTA leaves while a peer may still push into or signal it
   if (warp == kWbWarpMma) tmem_dealloc<512>(tmem);
   if (p.trace && threadIdx.x == 0) p.trace[2 * nt * 16 + blockIdx.x] = clock64() - t_cta0;
