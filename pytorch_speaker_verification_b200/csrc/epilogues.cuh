@@ -18,6 +18,7 @@ struct EpiStoreF32 {
     int N;
     int unpack_H;        // > 0: row m is a packed gate row (see lstm.cu); store to row gate*H + unit (direct path)
     int use_tma;
+    int64_t z_stride;    // elements between the outputs of consecutive blockIdx.z slices (split-K partials, direct path)
   };
   static constexpr int kInBytes = 0;
   static constexpr int kOutBytes = (BN / 32) * 16384;
@@ -40,7 +41,7 @@ struct EpiStoreF32 {
     }
     if (!valid) return;
     if (p.unpack_H > 0) m = ((m & 31) >> 3) * p.unpack_H + (m >> 5) * 8 + (m & 7);
-    float* dst = p.C + (int64_t)m * p.ldc + nc;
+    float* dst = p.C + (int64_t)blockIdx.z * p.z_stride + (int64_t)m * p.ldc + nc;
     for (int j = 0; j < 32; ++j)
       if (nc + j < p.N) dst[j] = acc[j] + (p.bias ? p.bias[nc + j] : 0.0f);
   }

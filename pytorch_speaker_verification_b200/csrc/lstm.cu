@@ -101,6 +101,7 @@ struct Work {
   float* xring[8];                  // persistent BPTT: dX ring of layer l >= 1, [3][nt][H/32][64 x 32] fp32
   unsigned *dcnt, *xcnt;            // persistent BPTT progress counters [L][nt], [L][H/32][nt]
   size_t bcnt_bytes;
+  float* wg_tmp;                    // weight gradients: the two split-K partial products [2][4H x H] fp32
   float* colsum_part;               // [chunks, 4H]
   float* gin_ring[8];               // persistent kernel: [kWlGinRing][nt][H/32][64 x 128] fp32 per layer
   unsigned *hcnt, *gcnt;            // persistent kernel: [L][nt] and [L][H/32][nt] progress counters
@@ -146,6 +147,7 @@ static Work layout_work(char* base, const Dims& d, int training) {
       w.dcl[l] = (float*)take(B * H * 4);
       w.xring[l] = l > 0 ? (float*)take((size_t)3 * nt * NS * 2048 * 4) : nullptr;
     }
+    w.wg_tmp = (float*)take((size_t)2 * 4 * H * H * 4);
     w.bcnt_bytes = al256((size_t)d.L * nt * 4) + al256((size_t)d.L * NS * nt * 4);
     w.dcnt = (unsigned*)take(w.bcnt_bytes);
     w.xcnt = w.dcnt + al256((size_t)d.L * nt * 4) / 4;
@@ -483,6 +485,12 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restric
 static void sgemm_small(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t s) {
   dim3 grid((N + 31) / 32, (M + 31) / 32);
   sgemm_small_kernel<<<grid, 256, 0, s>>>(A, B, C, M, N, K, ta, tb);
+}
+__global__ void add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
 }
 __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -825,7 +833,27 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       SVB_TRY(make_operand_map(&g.ta[0], w.gates[l], 4 * H, TB, 4 * H, 1, 0));
       SVB_TRY(make_operand_map(&g.tb[0], w.h_lo[l], H, TB, H, 1, 0));           // h_{t-1} (bf16): slots 0..T-1
       cudaError_t e;
-      if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
+      // 256 x 256 pair tiles need 64 B/clk of operands per SM (what one SM can pull from L2; 256 x 128 tiles need 96
+      // and ran at 67 % of the tensor peak); the 36 pair tiles of a 3072 x 768 product fill the machine only with the
+      // reduction split in two (gridDim.z), the halves are summed by a streaming kernel
+      const bool split2 = (H % 256 == 0) && TB >= 256;
+      auto wgrad_split2 = [&](GemmOperands& gg, float* out, int N) -> int {
+        gg.kz = 2; gg.K = ((TB + 1) / 2 + 63) / 64 * 64;    // slice 1 runs past T*B: the TMA zero-fills out-of-range rows
+        EpiStoreF32<256>::Params ep;
+        SVB_TRY(make_store_params<256>(&ep, w.wg_tmp, nullptr, 4 * H, N, (int64_t)N, H));
+        ep.z_stride = (int64_t)4 * H * N;
+        cudaError_t ee = launch_tc_gemm<256, 6, true, true, EpiStoreF32<256>, 8, 1, true>(gg, ep, s);
+        if (ee != cudaSuccess) { set_error("weight gradient (split-K pair tiles)", ee); return SVB_ERR_CUDA; }
+        const size_t n4 = (size_t)4 * H * N / 4;
+        add2_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(w.wg_tmp), reinterpret_cast<const float4*>(w.wg_tmp + 4 * (size_t)H * N),
+                                           reinterpret_cast<float4*>(out), n4);
+        gg.kz = 0; gg.K = TB;
+        return SVB_OK;
+      };
+      if (split2) {
+        SVB_TRY(wgrad_split2(g, grads[4 * l + 1], H));
+        e = cudaSuccess;
+      } else if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
         e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep, s);
@@ -837,7 +865,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
       SVB_TRY(make_operand_map(&g.tb[0], xin, lw.Ip, TB, lw.Ip, 1, 0));
-      if (lw.I % 128 == 0) {
+      if (split2 && lw.I % 256 == 0) {
+        SVB_TRY(wgrad_split2(g, grads[4 * l], lw.I));
+        e = cudaSuccess;
+      } else if (lw.I % 128 == 0) {
         EpiStoreF32<128>::Params ep2;
         SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
         e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep2, s);

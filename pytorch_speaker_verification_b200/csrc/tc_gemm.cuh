@@ -31,6 +31,8 @@ struct __align__(64) GemmOperands {
   int zb[kMaxTerms];
   int nterms;
   int f16;                       // operands are IEEE half instead of bf16 (same tensor maps: 2-byte elements)
+  int kz;                        // > 1: gridDim.z = kz slices of the reduction, K = length of ONE slice; slice z writes
+                                 // its partial product through Epi with blockIdx.z (see EpiStoreF32::z_stride)
   int M, N, K;                   // K = reduction length per term
   unsigned long long* trace;     // debug: 16 globaltimer stamps per CTA, or null
 };
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps) tc_gemm_kernel(const __gr
   const int n0 = (blockIdx.x / (TWO_CTA ? 2 : KSPLIT)) * BN;
   const int m0 = TWO_CTA ? (blockIdx.y * 2 + (blockIdx.x & 1)) * kBM : blockIdx.y * kBM;
   const int nkb = ((ops.K + kBK - 1) / kBK) / KSPLIT;            // host guarantees divisibility
-  const int kbase = kq * nkb * kBK;
+  const int kbase = kq * nkb * kBK + (int)blockIdx.z * ops.K;
   const int iters = nkb * ops.nterms;
   const int n_epi = KSPLIT > 1 ? n0 + 32 * kq : n0;              // first column this CTA's epilogue owns
   uint8_t* out_smem = smem + S::kRecvBytes;
@@ -353,7 +355,7 @@ cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& 
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(((ops.N + BN - 1) / BN) * KSPLIT, (ops.M + kBM - 1) / kBM);
+  cfg.gridDim = dim3(((ops.N + BN - 1) / BN) * KSPLIT, (ops.M + kBM - 1) / kBM, ops.kz > 1 ? ops.kz : 1);
   if (TWO_CTA) {       // x = 2 * n_tiles (pair rank in the low bit), y = pairs of 128-row tiles (odd tail: all OOB)
     cfg.gridDim.x *= 2;
     cfg.gridDim.y = (cfg.gridDim.y + 1) / 2;
