@@ -24,6 +24,7 @@
 //   xcnt[l][ns][j]   = T - t by X(l, u, s) (ns = 4 u + s) once dX of (t, j) is written
 // 30 clusters of 4 = 120 CTAs, all co-resident (cooperative launch).
 #pragma once
+#include <stdlib.h>
 
 constexpr int kWbTile = 64;
 constexpr int kWbKb = 12;              // 64-wide K blocks per CTA (K slice of 768)
@@ -568,8 +569,14 @@ static int launch_wbptt(WbParams& p, cudaStream_t s) {
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // Plain cluster launch by default: Nsight Compute refuses the cooperative + cluster combination (LaunchFailed), and
+  // the 30 clusters are co-resident anyway (one 640-thread, 218 KB CTA per SM; at most 33 four-CTA clusters fit the
+  // 148 SMs) as long as no other spinning kernel holds SMs.  Kernels of the same stream run before / after this one;
+  // CTAs of unrelated kernels on other streams finish and free their SMs.  A dependency that never arrives traps
+  // after the bounded spins instead of hanging.  SVB_COOPERATIVE_BPTT=1 adds the cooperative guarantee.
+  static const bool coop = getenv("SVB_COOPERATIVE_BPTT") != nullptr;
+  cfg.numAttrs = coop ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
-  if (e != cudaSuccess) { set_error("wbptt: cooperative cluster launch", e); return SVB_ERR_CUDA; }
+  if (e != cudaSuccess) { set_error("wbptt: cluster launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;
 }
