@@ -39,10 +39,17 @@ constexpr int kWbWarpTma = kWbEpiWarps, kWbWarpMma = kWbEpiWarps + 1, kWbWarpSto
               kWbWarpPoll = kWbEpiWarps + 3;   // lane 0: dependency poller, lane 1: epilogue-input loader
 constexpr int kWbAccCol = 384;
 // epilogue tiles (in place): gates / dG 2 x 8 KB boxes, c_t, c_{t-1}, dc
-constexpr int kWbOffG = 0, kWbOffCt = 16384, kWbOffCp = 24576, kWbOffDc = 32768, kWbStgBytes = 40960;
-constexpr int kWbRecvBytes = 3 * 8192;  // three peers' partial quarters: [slot][part 4][k 4][lane 32] float4
+// Three in-place buffers (gates -> dG 2 x 8 KB boxes, dc) + two read-only buffers (c_t, c_{t-1}): the in-place tiles
+// are busy from their TMA load through the gate math until their TMA store has drained (load latency + math + store
+// ~ 5000 cycles), which with two buffers alone bounded the tile period.
+constexpr int kWbOffG = 0, kWbOffDc = 16384, kWbIoBytes = 24576;       // per in-place buffer
+constexpr int kWbOffCt = 0, kWbOffCp = 8192, kWbCBytes = 16384;        // per read-only buffer
+constexpr int kWbStgBytes = 3 * kWbIoBytes + 2 * kWbCBytes;            // 104 KB
+// three peers' partial quarters, fp16: [slot][8-row group 8][lane 32] x 8 halves (16 B).  fp16 (2^-11) halves the DSMEM
+// traffic, which bounds the kernel; the partial sums are O(|dh|) and far from the fp16 range limits.
+constexpr int kWbRecvBytes = 3 * 4096;
 constexpr int kWbDhBytes = 8192;        // reduced dh tile [64 rows][32 units] fp32
-constexpr int kWbSmem = kWbStages * kWbStageBytes + 2 * kWbStgBytes + 2 * kWbRecvBytes + 2 * kWbDhBytes + 1024 + 1024;
+constexpr int kWbSmem = kWbStages * kWbStageBytes + kWbStgBytes + 2 * kWbRecvBytes + 2 * kWbDhBytes + 1024 + 1024;
 static_assert(kWbSmem <= 227 * 1024, "shared memory budget of the BPTT kernel");
 
 struct __align__(64) WbLayer {
@@ -94,6 +101,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+__device__ __forceinline__ void st_cluster_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 half2_to_float2(uint32_t h) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -120,16 +138,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint8_t* stg = ring + kWbStages * kWbStageBytes;
-  uint8_t* recv = stg + 2 * kWbStgBytes;
+  uint8_t* cst = stg + 3 * kWbIoBytes;         // the two c buffers
+  uint8_t* recv = stg + kWbStgBytes;
   uint8_t* dhb = recv + 2 * kWbRecvBytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(dhb + 2 * kWbDhBytes);
   uint64_t* empty = full + kWbStages;
   uint64_t* acc_full = empty + kWbStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2] 16 warps
-  uint64_t* in_full = acc_empty + 2;           // [2] epilogue input tiles landed (tx)
-  uint64_t* stg_full = in_full + 2;            // [2] 512 threads: outputs staged
-  uint64_t* stg_free = stg_full + 2;           // [2] store thread: staging buffer reusable
-  uint64_t* recv_full = stg_free + 2;          // [2] 12 remote warps: partial quarters of the three peers landed
+  uint64_t* in_full = acc_empty + 2;           // [3] epilogue input tiles landed (tx)
+  uint64_t* stg_full = in_full + 3;            // [3] 256 math threads: outputs staged (and c tiles read)
+  uint64_t* stg_free = stg_full + 3;           // [3] store thread: in-place buffer reusable
+  uint64_t* recv_full = stg_free + 3;          // [2] 6 remote warps: partial quarters of the three peers landed
   uint64_t* peer_free = recv_full + 2;         // [2] 12 remote warps: my three receivers consumed tile it-2
   uint64_t* dep_ready = peer_free + 2;         // [kWbDeps]
   uint64_t* dep_free = dep_ready + kWbDeps;    // [kWbDeps]
@@ -159,15 +178,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 8);               // the eight exchange warps
-      mbar_init(&in_full[b], 1);
-      mbar_init(&stg_full[b], 256);              // the eight math warps
-      mbar_init(&stg_free[b], 1);
       mbar_init(&recv_full[b], 6);               // 3 senders x 2 warps
       mbar_init(&peer_free[b], 6);               // 3 receivers x 2 owner warps
       mbar_init(&x_done[b], 64);
       mbar_init(&x_taken[b], 1);
       mbar_init(&dh_full[b], 64);
       mbar_init(&dh_free[b], 256);
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&in_full[b], 1);
+      mbar_init(&stg_full[b], 256);              // the eight math warps
+      mbar_init(&stg_free[b], 1);
     }
     for (int d = 0; d < kWbDeps; ++d) {
       mbar_init(&dep_ready[d], 1);
@@ -230,14 +251,18 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           const int d = (int)(it % kWbDeps);
           mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));   // our own dc store of frame t+1 is complete
           mbar_arrive(&dep_free[d]);
-          mbar_wait(&stg_free[buf], upar ^ 1);                       // the stores of tile it-2 have left the buffer
-          uint8_t* sb = stg + buf * kWbStgBytes;
-          mbar_expect_tx(&in_full[buf], kWbStgBytes);
-          tma_load_3d(sb + kWbOffG, &ly.t_dg, &in_full[buf], ns * 128, j * kWbTile, t);
-          tma_load_3d(sb + kWbOffG + 8192, &ly.t_dg, &in_full[buf], ns * 128 + 64, j * kWbTile, t);
-          tma_load_3d(sb + kWbOffCt, &ly.t_c, &in_full[buf], ns * 32, j * kWbTile, t + 1);
-          tma_load_3d(sb + kWbOffCp, &ly.t_c, &in_full[buf], ns * 32, j * kWbTile, t);
-          tma_load_3d(sb + kWbOffDc, &ly.t_dc, &in_full[buf], ns * 32, j * kWbTile, 0);
+          const int b3 = (int)(it % 3);
+          const uint32_t par3 = (uint32_t)((it / 3) & 1);
+          mbar_wait(&stg_free[b3], par3 ^ 1);                        // the stores of tile it-3 have left the buffer
+          if (it >= 2) mbar_wait(&stg_full[(it - 2) % 3], (uint32_t)(((it - 2) / 3) & 1));   // c buffer: math of it-2 done
+          uint8_t* sb = stg + b3 * kWbIoBytes;
+          uint8_t* cb = cst + buf * kWbCBytes;
+          mbar_expect_tx(&in_full[b3], kWbIoBytes + kWbCBytes);
+          tma_load_3d(sb + kWbOffG, &ly.t_dg, &in_full[b3], ns * 128, j * kWbTile, t);
+          tma_load_3d(sb + kWbOffG + 8192, &ly.t_dg, &in_full[b3], ns * 128 + 64, j * kWbTile, t);
+          tma_load_3d(cb + kWbOffCt, &ly.t_c, &in_full[b3], ns * 32, j * kWbTile, t + 1);
+          tma_load_3d(cb + kWbOffCp, &ly.t_c, &in_full[b3], ns * 32, j * kWbTile, t);
+          tma_load_3d(sb + kWbOffDc, &ly.t_dc, &in_full[b3], ns * 32, j * kWbTile, 0);
         }
       }
     }
@@ -351,10 +376,12 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
               mbar_wait_cluster(&peer_free[buf], upar ^ 1);
               if (warp == 1) WL_STAMP(13);
             }
-            const uint32_t dst = map_to_cta(recv_a + buf * kWbRecvBytes + ((s - q - 1) & 3) * 8192 + rg0 * 512 + lane * 16,
+            const uint32_t dst = map_to_cta(recv_a + buf * kWbRecvBytes + ((s - q - 1) & 3) * 4096 + (rg0 >> 1) * 512 + lane * 16,
                                             (uint32_t)q);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) st_cluster_f4(dst + k * 512, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            for (int k = 0; k < 2; ++k)
+              st_cluster_u4(dst + k * 512, make_uint4(pack_f16x2(v[8 * k], v[8 * k + 1]), pack_f16x2(v[8 * k + 2], v[8 * k + 3]),
+                                                      pack_f16x2(v[8 * k + 4], v[8 * k + 5]), pack_f16x2(v[8 * k + 6], v[8 * k + 7])));
             if (ps == 1) {
               __syncwarp();
               if (lane == 0) mbar_arrive_remote(&recv_full[buf], (uint32_t)q);
@@ -369,9 +396,11 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
 #pragma unroll
           for (int sl = 0; sl < 3; ++sl)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 r = lds_f4(recv_a + buf * kWbRecvBytes + sl * 8192 + (rg0 + k) * 512 + lane * 16);
-              v[4 * k] += r.x; v[4 * k + 1] += r.y; v[4 * k + 2] += r.z; v[4 * k + 3] += r.w;
+            for (int k = 0; k < 2; ++k) {
+              const uint4 r = lds_u4(recv_a + buf * kWbRecvBytes + sl * 4096 + ((rg0 >> 1) + k) * 512 + lane * 16);
+              const float2 a0 = half2_to_float2(r.x), a1 = half2_to_float2(r.y), a2 = half2_to_float2(r.z), a3 = half2_to_float2(r.w);
+              v[8 * k] += a0.x; v[8 * k + 1] += a0.y; v[8 * k + 2] += a1.x; v[8 * k + 3] += a1.y;
+              v[8 * k + 4] += a2.x; v[8 * k + 5] += a2.y; v[8 * k + 6] += a3.x; v[8 * k + 7] += a3.y;
             }
           if (ps == 1) {
             __syncwarp();
@@ -379,13 +408,15 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
             if (lane < 3) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
           }
           if (!is_R) {
-            // dX tile -> ring, fragment order [row group][lane] float4 = rows 4 rg .. 4 rg + 3 of unit `lane`
-            float4* xo = reinterpret_cast<float4*>(ly.xring) + ((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512 + rg0 * 32 + lane;
+            // dX tile, fragment order [row group][lane] float4 = rows 4 rg .. 4 rg + 3 of unit `lane`: staged in shared
+            // memory (the epilogue staging area is unused in X) and bulk-copied to the ring by the signal thread -- a
+            // gpu-scope fence in these two warps after direct global stores cost ~2000 cycles of the tile's chain
+            if (ps == 0) mbar_wait(&x_taken[buf], upar ^ 1);       // the copy of tile it-2 has left the buffer
+            const uint32_t xo = smem_u32(stg) + buf * 8192 + (rg0 * 32 + lane) * 16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) xo[k * 32] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            for (int k = 0; k < 4; ++k) sts_f4(xo + k * 512, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
             if (ps == 1) {
-              fence_acq_rel_gpu();
-              mbar_wait(&x_taken[buf], upar ^ 1);
+              fence_proxy_async_smem();
               mbar_arrive(&x_done[buf]);
             }
             continue;
@@ -435,9 +466,12 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           long long* tr = (trace_cta && t == T / 2 && threadIdx.x == 256) ? trace_cta + j * 16 : nullptr;
           WL_STAMP(9);
           mbar_wait(&dh_full[buf], upar);
-          mbar_wait(&in_full[buf], upar);
+          const int b3 = (int)(it % 3);
+          const uint32_t par3 = (uint32_t)((it / 3) & 1);
+          mbar_wait(&in_full[b3], par3);
           WL_STAMP(10);
-          const uint32_t sb = stg_a + buf * kWbStgBytes;
+          const uint32_t sb = stg_a + b3 * kWbIoBytes;
+          const uint32_t cb = stg_a + 3 * kWbIoBytes + buf * kWbCBytes;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int ug = (mt & 3) * 2 + hh;      // units 4 ug .. 4 ug + 3 of the CTA's 32
@@ -445,7 +479,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
             const uint32_t g_off = (G >> 1) * 8192 + row * 128 + 8 * (ug & 1);
             const uint32_t u_off = row * 128 + ((ug ^ (row & 7)) << 4);
             const float4 dh4 = lds_f4(dh_a + buf * kWbDhBytes + row * 128 + ug * 16);
-            const float4 ct4 = lds_f4(sb + kWbOffCt + u_off), cp4 = lds_f4(sb + kWbOffCp + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
+            const float4 ct4 = lds_f4(cb + kWbOffCt + u_off), cp4 = lds_f4(cb + kWbOffCp + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
             uint32_t gaddr[4];
             uint2 gq[4];
 #pragma unroll
@@ -485,7 +519,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           }
           mbar_arrive(&dh_free[buf]);
           fence_proxy_async_smem();
-          mbar_arrive(&stg_full[buf]);
+          mbar_arrive(&stg_full[b3]);
           WL_STAMP(11);
         }
       }
@@ -505,9 +539,16 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     // ------------------------------------------------------------------ signal warp (X): publish dX tiles
     if (lane == 0) {
       for (long long it = 0; it < total; ++it) {
-        mbar_wait(&x_done[it & 1], (uint32_t)((it >> 1) & 1));
-        mbar_arrive(&x_taken[it & 1]);
-        st_relaxed(p.xcnt + ((size_t)l * NS + ns) * nt + (it % nt), (unsigned)(it / nt + 1));
+        const int buf = (int)(it & 1);
+        const int t = T - 1 - (int)(it / nt), j = (int)(it % nt);
+        mbar_wait(&x_done[buf], (uint32_t)((it >> 1) & 1));
+        float* dst = ly.xring + (((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512) * 4;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg) + buf * 8192),
+                     "n"(8192) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        mbar_arrive(&x_taken[buf]);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.xcnt + ((size_t)l * NS + ns) * nt + j), "r"((unsigned)(it / nt + 1)) : "memory");
       }
     }
   } else if (warp == kWbWarpStore && is_R) {
@@ -518,14 +559,15 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         for (int j = 0; j < nt; ++j, ++it) {
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
-          mbar_wait(&stg_full[buf], upar);
-          const uint8_t* sb = stg + buf * kWbStgBytes;
+          const int b3 = (int)(it % 3);
+          mbar_wait(&stg_full[b3], (uint32_t)((it / 3) & 1));
+          const uint8_t* sb = stg + b3 * kWbIoBytes;
           tma_store_3d(&ly.t_dg, sb + kWbOffG, ns * 128, j * kWbTile, t);
           tma_store_3d(&ly.t_dg, sb + kWbOffG + 8192, ns * 128 + 64, j * kWbTile, t);
           tma_store_3d(&ly.t_dc, sb + kWbOffDc, ns * 32, j * kWbTile, 0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          mbar_arrive(&stg_free[buf]);
+          mbar_arrive(&stg_free[b3]);
           red_release_add(p.dcnt + l * nt + j, 1u);      // release: see wlstm.cuh
           if (trace_cta && t == T / 2) trace_cta[j * 16 + 15] = clock64();
         }
