@@ -297,8 +297,11 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     const uint32_t desc_lo0 = (uint32_t)desc0, desc_hi = (uint32_t)(desc0 >> 32);
     int stage = 0;
     uint32_t phase = 0;
-    const long long my_total = elect_one() ? total : 0;
-    for (long long it = 0; it < my_total; ++it) {
+    // `if (elect_one())` around the loop, NOT a per-thread trip count: with `n = elect_one() ? total : 0; for (it < n)`
+    // the compiler treats the body as divergent code and wraps EVERY tcgen05.mma in an elect / R2UR.BROADCAST /
+    // BRA.U.ANY loop (~12 instructions, 60-70 cycles of issue per MMA instead of 32).
+    if (elect_one())
+    for (long long it = 0; it < total; ++it) {
       const int buf = (int)(it & 1);
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;

@@ -283,8 +283,11 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     uint32_t phase = 0;
     // ONE thread runs the whole loop (waits included): looping the whole warp with an election and a __syncwarp per
     // group costs +150 cycles per group of 8 MMAs (256 cycles of tensor work), scripts/ubench/mma_issue.cu
-    const long long my_total = elect_one() ? total : 0;
-    for (long long it = 0; it < my_total; ++it) {
+    // `if (elect_one())` around the loop, NOT a per-thread trip count: with `n = elect_one() ? total : 0; for (it < n)`
+    // the compiler treats the body as divergent code and wraps EVERY tcgen05.mma in an elect / R2UR.BROADCAST /
+    // BRA.U.ANY loop (~12 instructions, 60-70 cycles of issue per MMA instead of 32).
+    if (elect_one())
+    for (long long it = 0; it < total; ++it) {
       const int buf = (int)(it & 1);
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       long long* tr = (trace_cta && it / nt == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;

@@ -1,0 +1,27 @@
+"""Dev: time the persistent BPTT kernel with parts switched off (results are garbage in those runs)."""
+import sys
+import torch
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import _inputs as I
+import pytorch_speaker_verification_b200 as svb
+from pytorch_speaker_verification_b200 import _lib
+L = _lib.lib()
+torch.manual_seed(0)
+net = svb.SpeechEmbedder().cuda()
+x = torch.tensor(I.logmel(640, 160, seed=1234)).cuda()
+import ctypes
+buf = (ctypes.c_float * 16)()
+for mask in (0, 1, 2, 4, 16, 32, 8, 63, 55, 47):
+    res = []
+    for rep in range(3):
+        net.zero_grad()
+        L.svb_set_ablate(0)
+        e = net(x); loss = e.square().sum()
+        L.svb_set_ablate(mask)
+        L.svb_profile_enable(1)
+        loss.backward()
+        torch.cuda.synchronize()
+        L.svb_profile_read(buf, 16)
+        res.append(buf[5])
+    print(f"ablate={mask:3d} (1 MMA, 2 math, 4 operand loads, 16 DSMEM payload, 32 input loads, 8 deps): BPTT kernel {min(res):.3f} ms", flush=True)
+L.svb_set_ablate(0); L.svb_profile_enable(0)
