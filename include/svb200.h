@@ -74,6 +74,7 @@ int svb_set_persistent_bwd(int on);
 /* Debug hooks of the persistent kernels (timing experiments only): ablation mask (results become garbage) and
  * clock64 trace buffers (device pointers, or NULL). */
 int svb_set_ablate(int mask);
+int svb_set_trace_mode(int mode);   /* 1: per-tile stamps of frame T/2, 2: per-role wait accounting (scripts/account_wlstm.py) */
 int svb_set_trace(unsigned long long* device_buffer);
 int svb_set_trace_bwd(unsigned long long* device_buffer);
 

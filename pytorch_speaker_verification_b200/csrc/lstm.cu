@@ -546,6 +546,7 @@ static int g_persistent = 1;   // persistent wavefront forward kernel (wlstm.cuh
 static int g_persistent_bwd = 1;   // persistent wavefront BPTT kernel (wbptt.cuh) when the shape allows
 static int g_fwd_pair = 0;     // forward frame: CTA pairs share the W_hh slice (measured slower: cluster barriers outweigh the ingest saving)
 static int g_bwd_splitk = 1;   // BPTT frame: 4-CTA cluster split-K with DSMEM partial exchange
+static int g_trace_mode = 1;  // debug: 1 per-tile stamps, 2 wait accounting (persistent forward kernel)
 static int g_ablate = 0;      // debug: persistent kernel ablation mask (timing experiments only)
 static unsigned long long* g_trace_bwd = nullptr;   // debug: stamps of the persistent BPTT kernel
 static unsigned long long* g_trace = nullptr;   // debug: device buffer for per-CTA timestamps of the frame kernels
@@ -582,6 +583,7 @@ extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_O
 extern "C" int svb_set_persistent_bwd(int on) { g_persistent_bwd = on != 0; return SVB_OK; }
 extern "C" int svb_set_fwd_pair(int on) { g_fwd_pair = on != 0; return SVB_OK; }
 extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
+extern "C" int svb_set_trace_mode(int mode) { g_trace_mode = mode; return SVB_OK; }
 extern "C" int svb_set_ablate(int mask) { g_ablate = mask; return SVB_OK; }
 extern "C" int svb_set_trace_bwd(unsigned long long* buf) { g_trace_bwd = buf; return SVB_OK; }
 extern "C" int svb_set_trace(unsigned long long* buf) { g_trace = buf; return SVB_OK; }
@@ -677,6 +679,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     wp.hcnt = w.hcnt; wp.gcnt = w.gcnt; wp.h_last = w.h_last;
     wp.trace = reinterpret_cast<long long*>(g_trace);
     wp.ablate = g_ablate;
+    wp.trace_mode = g_trace_mode;
     wp.B = B; wp.T = T; wp.L = L; wp.H = H; wp.nt = nt; wp.training = training;
     cudaMemsetAsync(w.hcnt, 0, w.cnt_bytes, s);
     SVB_TRY(H == 768 ? launch_wlstm_fwd<768>(wp, s) : H == 512 ? launch_wlstm_fwd<512>(wp, s) : launch_wlstm_fwd<256>(wp, s));

@@ -73,8 +73,11 @@ struct __align__(64) WlstmParams {
   long long* trace;        // debug: clock64 stamps of R(1,0) and P(1,0) at frame T/2 ([2][nt][16]), or null
   int B, T, L, H, nt, training;
   int ablate;              // debug: 1 skip MMAs, 2 skip epilogue math, 4 skip operand loads (results are garbage)
+  int trace_mode;          // 1: per-tile stamps of frame T/2 (perturbs the traced CTAs); 2: wait accounting only
 };
 #define WL_STAMP(slot) do { if (tr) tr[(slot)] = clock64(); } while (0)
+// wait accounting (debug, p.trace_mode == 2): cycles a role thread spends in a statement, accumulated in a register
+#define WL_ACC(var, ...) do { if (acct) { const long long a0_ = clock64(); __VA_ARGS__; var += clock64() - a0_; } else { __VA_ARGS__; } } while (0)
 
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -149,7 +152,12 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
   const int ngroups = (nkb + kWlKbPerStage - 1) / kWlKbPerStage;
   const int nt = p.nt, T = p.T;
   const long long total = (long long)T * nt;
-  long long* const trace_cta = (p.trace && l == 1 && n == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+  long long* const trace_cta = (p.trace && p.trace_mode != 2 && l == 1 && n == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+  // accounting: CTAs R(0,0), R(1,0), P(1,0) -> rows 0, 1, 2 of 64 slots each at p.trace + 8192
+  const int acct_row = (n == 0 && is_R && l == 0) ? 0 : (n == 0 && is_R && l == 1) ? 1 : (n == 0 && !is_R && l == 1) ? 2 : -1;
+  const bool acct = p.trace && p.trace_mode == 2 && acct_row >= 0;
+  long long* const acct_out = p.trace + 8192 + (acct_row < 0 ? 0 : acct_row) * 64;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWlStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -205,7 +213,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       for (int t = 0; t < T; ++t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int d = (int)(it % kWlDeps);
-          mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1));
+          WL_ACC(w0, mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1)));
+          const long long pa0 = acct ? clock64() : 0;
           if (p.ablate & 8) {
           } else if (is_R) {
             wait_two_counters(t > 0 ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * t),
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
             wait_two_counters(l > 0 ? p.hcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (t + 1)),
                               t >= kWlGinRing ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * (t - kWlGinRing + 1)));
           }
+          if (acct) w1 += clock64() - pa0;
           mbar_arrive(&dep_ready[d]);
         }
       }
@@ -229,9 +239,9 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
           const int d = (int)(it % kWlDeps);
-          mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));   // our own stores of frame t-1 are complete
+          WL_ACC(w0, mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1)));   // our own stores of frame t-1 are complete
           mbar_arrive(&dep_free[d]);
-          mbar_wait(&stg_full[buf], upar ^ 1);                       // the epilogue of tile it-2 has read its c tile
+          WL_ACC(w1, mbar_wait(&stg_full[buf], upar ^ 1));                       // the epilogue of tile it-2 has read its c tile
           mbar_expect_tx(&cin_full[buf], kWlCinBytes);
           tma_load_3d(cin + buf * kWlCinBytes, &ly.t_c, &cin_full[buf], n * 32, j * kWlTile, p.training ? t : (t & 1));
         }
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           const int d = (int)(it % kWlDeps);
           long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
           WL_STAMP(0);
-          mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));
+          WL_ACC(w0, mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1)));
           mbar_arrive(&dep_free[d]);
           WL_STAMP(1);
           const CUtensorMap* tm = is_R ? &ly.t_h : &ly.t_in;
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           for (int gi = 0; gi < ngroups; ++gi) {
             const int kb0 = gi * kWlKbPerStage;
             const int nk = nkb - kb0 < kWlKbPerStage ? nkb - kb0 : kWlKbPerStage;
-            mbar_wait(&empty[stage], phase ^ 1);
+            WL_ACC(w1, mbar_wait(&empty[stage], phase ^ 1));
             if (p.ablate & 4) {
               mbar_arrive(&full[stage]);
               if (++stage == kWlStages) { stage = 0; phase ^= 1; }
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       long long* tr = (trace_cta && it / nt == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;
       WL_STAMP(3);
-      mbar_wait(&acc_empty[buf], upar ^ 1);
+      WL_ACC(w0, mbar_wait(&acc_empty[buf], upar ^ 1));
       tc_fence_after();
       WL_STAMP(4);
       for (int gi = 0; gi < ngroups; ++gi) {
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         const int nk = nkb - kb0 < kWlKbPerStage ? nkb - kb0 : kWlKbPerStage;
         long long* trd = tr ? tr + 3 * nt * 16 : nullptr;      // MMA detail rows
         if (trd && gi < 6) trd[2 * gi] = clock64();
-        mbar_wait(&full[stage], phase);
+        WL_ACC(w1, mbar_wait(&full[stage], phase));
         tc_fence_after();
         if (trd && gi < 6) trd[2 * gi + 1] = clock64();
         if (gi == 0) WL_STAMP(5);
@@ -367,12 +377,12 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       WL_STAMP(7);
       if (is_R) {
         const int d = (int)(it % kWlDeps);
-        mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1));     // gin of (t, j) is published
+        WL_ACC(w0, mbar_wait(&dep_ready[d], (uint32_t)((it / kWlDeps) & 1)));     // gin of (t, j) is published
 #pragma unroll
         for (int k = 0; k < 4; ++k) gv[k] = __ldcg(gfrag + k * 128);
       }
       WL_STAMP(8);
-      mbar_wait(&acc_full[buf], upar);
+      WL_ACC(w1, mbar_wait(&acc_full[buf], upar));
       tc_fence_after();
       WL_STAMP(9);
       float a0[16], a1[16];
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(&dep_free[(int)(it % kWlDeps)]);
           WL_STAMP(10);
-          mbar_wait(&stg_free[buf], upar ^ 1);    // staging buffer drained by the store warp
+          WL_ACC(w2, mbar_wait(&stg_free[buf], upar ^ 1));    // staging buffer drained by the store warp
           WL_STAMP(11);
         }
         if (p.ablate & 2) continue;
@@ -444,7 +454,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           vg[k] = g1 ? p1lo : s0; vo[k] = g1 ? p1hi : s1;
         }
         if (ps == 0) {
-          mbar_wait(&cin_full[buf], upar);        // c_{t-1} tile landed
+          WL_ACC(w3, mbar_wait(&cin_full[buf], upar));        // c_{t-1} tile landed
           WL_STAMP(12);
         }
         // all loads, then the math, then all stores
@@ -486,7 +496,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // ------------------------------------------------------------------ signal warp (P): publish gin tiles
     if (lane == 0) {
       for (long long it = 0; it < total; ++it) {
-        mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1));
+        WL_ACC(w0, mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1)));
         mbar_arrive(&gin_taken[it & 1]);
         st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + (it % nt), (unsigned)(it / nt + 1));
       }
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         for (int j = 0; j < nt; ++j, ++it) {
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
-          mbar_wait(&stg_full[buf], upar);
+          WL_ACC(w0, mbar_wait(&stg_full[buf], upar));
           long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
           WL_STAMP(14);
           const uint8_t* sb = stg + buf * kWlStgBytes;
@@ -517,12 +527,27 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           // with a NaN-poisoned workspace, tests/test_gpu_parity.py::test_persistent_kernel_no_stale_reads).  One
           // fence is enough and costs nothing at the current period; proxy fence + __threadfence + release together
           // cost ~3000 cycles per tile and made this warp the limiter.
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          WL_ACC(w1, asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"));
           mbar_arrive(&stg_free[buf]);
-          red_release_add(p.hcnt + l * nt + j, 1u);
+          WL_ACC(w2, red_release_add(p.hcnt + l * nt + j, 1u));
           WL_STAMP(15);
         }
       }
+    }
+  }
+  if (acct) {
+    // slots: 8 per role thread: poller 0, c-loader 1, producer 2, mma 3, store/signal 4, epilogue warp 0 -> 5, warp 8 -> 6
+    int role = -1;
+    if (warp == kWlWarpPoll && lane == 0) role = 0;
+    else if (warp == kWlWarpPoll && lane == 1) role = 1;
+    else if (warp == kWlWarpTma && (w0 | w1)) role = 2;
+    else if (warp == kWlWarpMma && (w0 | w1)) role = 3;
+    else if (warp == kWlWarpStore && (w0 | w1 | w2)) role = 4;
+    else if (threadIdx.x == 0) role = 5;
+    else if (threadIdx.x == 256) role = 6;
+    if (role >= 0) {
+      acct_out[role * 8 + 0] = w0; acct_out[role * 8 + 1] = w1; acct_out[role * 8 + 2] = w2; acct_out[role * 8 + 3] = w3;
+      acct_out[role * 8 + 4] = clock64() - t_cta0;
     }
   }
   tc_fence_before();
