@@ -400,7 +400,10 @@ def main():
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
                          # (profiles/r1_ncu_full_summary.txt); the frame kernels' writes stay in the 126 MB L2
-                         "traffic": {"recurrent_bwd": 18506752}.get(dom),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                         # (profiles/r1b_ncu_full_persistent_summary.txt)
+                         "traffic": {"recurrent_bwd": 2940671000 + 2289802000,
+                                     "recurrent_fwd": 1238112000 + 7455558000}.get(dom) if args.recurrent_terms == 1 else None,
                          "peak_source": f"{pk_src} (sustained bf16)",
                          "avg_launch_us": avg_ms * 1e3, "launches_per_step": launches,
                          # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)

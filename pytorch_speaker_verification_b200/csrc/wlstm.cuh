@@ -76,8 +76,13 @@ struct __align__(64) WlstmParams {
   int trace_mode;          // 1: per-tile stamps of frame T/2 (perturbs the traced CTAs); 2: wait accounting only
 };
 #define WL_STAMP(slot) do { if (tr) tr[(slot)] = clock64(); } while (0)
-// wait accounting (debug, p.trace_mode == 2): cycles a role thread spends in a statement, accumulated in a register
+// wait accounting (debug; compile with -DSVB_WL_ACCOUNT and set trace_mode 2): cycles a role thread spends in a
+// statement, accumulated in a register.  Off by default: the accumulators cost the epilogue warps registers (spills).
+#ifdef SVB_WL_ACCOUNT
 #define WL_ACC(var, ...) do { if (acct) { const long long a0_ = clock64(); __VA_ARGS__; var += clock64() - a0_; } else { __VA_ARGS__; } } while (0)
+#else
+#define WL_ACC(var, ...) do { __VA_ARGS__; } while (0)
+#endif
 
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -155,9 +160,14 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
   long long* const trace_cta = (p.trace && p.trace_mode != 2 && l == 1 && n == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
   // accounting: CTAs R(0,0), R(1,0), P(1,0) -> rows 0, 1, 2 of 64 slots each at p.trace + 8192
   const int acct_row = (n == 0 && is_R && l == 0) ? 0 : (n == 0 && is_R && l == 1) ? 1 : (n == 0 && !is_R && l == 1) ? 2 : -1;
+#ifdef SVB_WL_ACCOUNT
   const bool acct = p.trace && p.trace_mode == 2 && acct_row >= 0;
   long long* const acct_out = p.trace + 8192 + (acct_row < 0 ? 0 : acct_row) * 64;
   long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#else
+  constexpr bool acct = false;
+  (void)acct_row;
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWlStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -214,7 +224,9 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         for (int j = 0; j < nt; ++j, ++it) {
           const int d = (int)(it % kWlDeps);
           WL_ACC(w0, mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1)));
+#ifdef SVB_WL_ACCOUNT
           const long long pa0 = acct ? clock64() : 0;
+#endif
           if (p.ablate & 8) {
           } else if (is_R) {
             wait_two_counters(t > 0 ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * t),
@@ -223,7 +235,9 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
             wait_two_counters(l > 0 ? p.hcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (t + 1)),
                               t >= kWlGinRing ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * (t - kWlGinRing + 1)));
           }
+#ifdef SVB_WL_ACCOUNT
           if (acct) w1 += clock64() - pa0;
+#endif
           mbar_arrive(&dep_ready[d]);
         }
       }
@@ -535,6 +549,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       }
     }
   }
+#ifdef SVB_WL_ACCOUNT
   if (acct) {
     // slots: 8 per role thread: poller 0, c-loader 1, producer 2, mma 3, store/signal 4, epilogue warp 0 -> 5, warp 8 -> 6
     int role = -1;
@@ -550,6 +565,7 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       acct_out[role * 8 + 4] = clock64() - t_cta0;
     }
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == kWlWarpMma) tmem_dealloc<512>(tmem);
