@@ -492,6 +492,13 @@ __global__ void add2_kernel(const float4* __restrict__ a, const float4* __restri
     out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
   }
 }
+__global__ void sumz_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n, int kz) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < kz; ++z) acc += part[(size_t)z * n + i];
+  out[i] = acc;
+}
 __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -876,9 +883,22 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
         e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep2, s);
       } else {
+        // narrow input (layer 0: N = 40): only 4H/128 = 24 output tiles, so the reduction over T*B is split over
+        // gridDim.z (144 CTAs at 4H = 3072) and the partial products are summed by a streaming kernel
+        int kz = 1;
+        if (TB >= 4096 && (size_t)4 * H * lw.I * 6 <= (size_t)2 * 4 * H * H) kz = 6;
         EpiStoreF32<128>::Params ep2;
-        SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        SVB_TRY(make_store_params<128>(&ep2, kz > 1 ? w.wg_tmp : grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        if (kz > 1) {
+          g.kz = kz; g.K = ((TB + kz - 1) / kz + 63) / 64 * 64;     // the last slices run past T*B: TMA zero-fill
+          ep2.z_stride = (int64_t)4 * H * lw.I;
+        }
         e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
+        if (kz > 1 && e == cudaSuccess) {
+          const size_t n = (size_t)4 * H * lw.I;
+          sumz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.wg_tmp, grads[4 * l], n, kz);
+          g.kz = 0; g.K = TB;
+        }
       }
       if (e != cudaSuccess) { set_error("dW_ih", e); return SVB_ERR_CUDA; }
     }
