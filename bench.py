@@ -200,8 +200,26 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
                   "sweep_GBps": sim.numel() * 4 / (ms * 1e-3) / 1e9, "cossim_from_embeddings_us": ms_cos * 1e3,
                   "eer": float(res[0])}
 
-    # ---- fused GE2E forward+backward alone (raw C ABI, preallocated buffers)
-    for (Ns, Ms) in ((64, 10), (512, 10)):
+    # ---- fused GE2E forward+backward alone (raw C ABI, preallocated buffers).  Device time per launch: 20 calls
+    # captured in a CUDA graph and replayed (a 15 us kernel is shorter than the ctypes + cooperative-launch host
+    # path, so a plain loop would time the host); the plain loop is reported next to it.
+    def graph_time(fn, reps=20, n=20):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(reps):
+                        fn()
+            torch.cuda.current_stream().wait_stream(side)
+            return dev_time(g.replay, n, 3) / reps
+        except Exception as exc:          # capture of cooperative launches unsupported: report the loop only
+            torch.cuda.synchronize()
+            return None
+
+    for (Ns, Ms, mode, tag) in ((64, 10, 1, ""), (64, 10, 2, "_general_kernel"), (512, 10, 1, "")):
         Eg = torch.tensor(I.ge2e_embeddings(Ns, Ms, 256, "unit")).to(dev)
         w = torch.tensor(10.0, device=dev)
         b = torch.tensor(-5.0, device=dev)
@@ -212,11 +230,18 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
         dE = torch.empty_like(Eg)
         dw = torch.empty((), device=dev)
         db = torch.empty((), device=dev)
-        ms = dev_time(lambda: L.svb_ge2e(ptr(Eg), None, Ns, Ms, 256, Ns, ptr(w), ptr(b), None, None, None, None,
-                                         ptr(loss), ptr(dE), None, ptr(dw), ptr(db), ptr(ws),
-                                         ctypes.c_size_t(nb.value), 1, st), 100, 10)
-        out[f"ge2e_fwd_bwd_N{Ns}"] = {"us": ms * 1e3, "algorithmic_bytes": 2 * Eg.numel() * 4,
-                                      "GBps": 2 * Eg.numel() * 4 / (ms * 1e-3) / 1e9}
+
+        def call():
+            L.svb_ge2e(ptr(Eg), None, Ns, Ms, 256, Ns, ptr(w), ptr(b), None, None, None, None, ptr(loss), ptr(dE),
+                       None, ptr(dw), ptr(db), ptr(ws), ctypes.c_size_t(nb.value), mode, stream_ptr())
+
+        ms_loop = dev_time(call, 100, 10)
+        ms_graph = graph_time(call)
+        ms = ms_graph if ms_graph is not None else ms_loop
+        out[f"ge2e_fwd_bwd_N{Ns}{tag}"] = {"us": ms * 1e3, "us_call_loop": ms_loop * 1e3,
+                                           "timing": "cuda graph replay" if ms_graph is not None else "call loop",
+                                           "algorithmic_bytes": 2 * Eg.numel() * 4,
+                                           "GBps": 2 * Eg.numel() * 4 / (ms * 1e-3) / 1e9}
     return out
 
 

@@ -94,7 +94,9 @@ int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);
  *   gscale device scalar multiplying every gradient or NULL.
  * Outputs (any may be NULL): cos_out (N,M,Nc) incl. the +1e-6 of utils.py:114; per_out (N,M) per-embedding loss;
  *   loss_out scalar (SUM, utils.py:131); dE (N,M,D); dCext (Nc,D); dw, db scalars.
- * fused != 0: single cooperative launch; 0: one launch per phase (debug). */
+ * fused = 1: single cooperative launch; loss batches with N <= #SMs, M <= 16, D % 4 == 0 (the reference's training
+ *   batches) take the one-CTA-per-speaker kernel (3 phases, 2 grid barriers), everything else the general 5-phase
+ *   kernel; fused = 2: always the general kernel; 0: one launch per phase (debug). */
 int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w, const float* b,
              const float* dcos, const float* gscale, float* cos_out, float* per_out, float* loss_out, float* dE,
              float* dCext, float* dw, float* db, void* workspace, size_t workspace_bytes, int fused, void* stream);
@@ -109,6 +111,19 @@ int svb_calc_loss(const float* S, int N, int M, int Nc, float* per_out, float* l
 
 /* x[i] *= *g for three buffers in one launch (autograd's upstream scalar). */
 int svb_scale3(float* a, size_t na, float* b, size_t nb, float* c, size_t nc, const float* g, void* stream);
+
+/* ---- optimizer tail of the training step (train_speech_embedder.py:33-36,63-65) ----- */
+
+int svb_clip_sgd_workspace_bytes(size_t* bytes);
+/* clip_grad_norm_ per clip group followed by the plain SGD step, two launches for all tensors:
+ *   total_norm_g = sqrt(sum over the group's tensors of sum g^2); coef_g = min(1, max_norm_g / (total_norm_g + 1e-6));
+ *   g <- coef_g * g (stored only if write_clipped_grads != 0, as clip_grad_norm_ does in place); p <- p - lr * g.
+ * params/grads: HOST arrays of n_tensors (<= 32) DEVICE float32 pointers; numel, group (clip group of each tensor,
+ * < n_groups <= 4) and max_norm (per group; <= 0 disables clipping) are HOST arrays; norms_out (device, n_groups
+ * floats, may be NULL) receives the pre-clip total norms that clip_grad_norm_ returns. */
+int svb_clip_sgd(void* const* params, void* const* grads, const int64_t* numel, const int32_t* group, int n_tensors,
+                 const float* max_norm, int n_groups, float lr, int write_clipped_grads, float* norms_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- TI-SV EER sweep (train_speech_embedder.py:132-149) ---------------------------------------------------------- */
 

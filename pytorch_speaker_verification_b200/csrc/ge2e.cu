@@ -428,7 +428,320 @@ __global__ void __launch_bounds__(kThreads) ge2e_phase_kernel(const Ge2eArgs a, 
   else phase_d(a, smem);
 }
 
+// ---------------------------------------------------------------------------------------------- small-batch kernel
+// One CTA per speaker, three phases, two grid barriers (the training batch of the reference, N = 64 x M = 10, is far
+// too small for five phases of tiled GEMMs: the general kernel above spends its time in barriers and L2 round trips).
+//   1  CTA j: its M rows -> utterance sum, unit centroid c^_j (published: N x D floats is all the other CTAs need),
+//      per-row norms, leave-one-out cosine, e^ (kept in shared memory for the whole kernel)
+//   2  CTA j: all unit centroids -> shared memory; cos for its M rows, softmax, A = wG; R = A_off C^ stays on chip;
+//      its contribution to every centroid's P_k = sum_rows A_off e^ goes to a [j][k][D] slab (fixed-order sum later)
+//   3  CTA k: P_k = sum_j slab[j][k], dC_k, and dE of its own rows (everything else is still in shared memory)
+// Eligibility (svb_ge2e, fused == 1): own centroids, loss mode, M <= 16, D % 4 == 0, N <= #SMs, shared memory fits.
+constexpr int kST = 512;
+constexpr int kSW = kST / 32;
+constexpr int kSpkMaxN = 148;
+constexpr int kSpkMaxM = 16;
+
+__device__ float block_sum_s(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSW; ++i) t += red[i];
+  return t;
+}
+
+struct SpkLayout {
+  int Npad, LDC, KB, DS, KH, U;   // U = floats of the aliased scratch region
+  size_t floats;
+};
+__host__ __device__ inline SpkLayout spk_layout(int N, int D, int MP) {
+  SpkLayout l;
+  l.Npad = (N + 3) & ~3;
+  l.LDC = D + 4;
+  l.KB = (N + 31) / 32;
+  int ds = kSW / l.KB;
+  if (ds < 1) ds = 1;
+  if (ds > D / 4) ds = D / 4;
+  l.DS = ds;
+  l.KH = D >= kST ? 1 : kST / D;
+  const int u1 = l.DS * MP * l.Npad;
+  const int u2 = l.KH * MP * D;
+  l.U = u1 > u2 ? u1 : u2;
+  l.floats = (size_t)l.Npad * l.LDC     // Ch
+             + 2 * (size_t)MP * D       // rE, rH
+             + (size_t)l.U              // cos partials | R partials
+             + 2 * (size_t)MP * l.Npad  // cosr, At
+             + 2 * (size_t)D            // s, Pv
+             + (size_t)(l.KH * D)       // Pq
+             + 5 * (size_t)MP + 32;     // ine, inu, cosd, adiag, rr, red
+  return l;
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  cg::grid_group grid = cg::this_grid();
+  const int N = a.N, M = a.M, D = a.D, NM = N * M, D4 = D / 4;
+  const SpkLayout L = spk_layout(N, D, MP);
+  float* Ch = smem;
+  float* rE = Ch + (size_t)L.Npad * L.LDC;
+  float* rH = rE + MP * D;
+  float* U = rH + MP * D;
+  float* cosr = U + L.U;
+  float* At = cosr + MP * L.Npad;
+  float* s = At + MP * L.Npad;
+  float* Pv = s + D;
+  float* Pq = Pv + D;
+  float* ine = Pq + L.KH * D;
+  float* inu = ine + MP;
+  float* cosd = inu + MP;
+  float* adiag = cosd + MP;
+  float* rr = adiag + MP;
+  float* red = rr + MP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = blockIdx.x;
+  const size_t row0 = (size_t)j * M;
+  const float invM = 1.0f / (float)M, invM1 = 1.0f / (float)(M - 1);
+
+  // ------------------------------------------------------------------ phase 1
+  {
+    const float4* Ej = reinterpret_cast<const float4*>(a.E + row0 * D);
+    float4* rE4 = reinterpret_cast<float4*>(rE);
+    for (int i = tid; i < MP * D4; i += kST) rE4[i] = (i < M * D4) ? Ej[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < MP * L.Npad; i += kST) At[i] = 0.f;
+  }
+  __syncthreads();
+  float cc = 0.f;
+  for (int d = tid; d < D; d += kST) {
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc += rE[m * D + d];
+    s[d] = acc;
+    const float c = acc * invM;
+    cc += c * c;
+  }
+  cc = block_sum_s(cc, red);
+  const float incj = 1.0f / fmaxf(sqrtf(cc), kCosEps);
+  for (int d = tid; d < D; d += kST) a.Chat[(size_t)j * D + d] = s[d] * invM * incj;
+  for (int m = warp; m < MP; m += kSW) {
+    if (m < M) {
+      const float* e = rE + m * D;
+      float ee = 0.f, uu = 0.f, eu = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float x = e[d];
+        const float u = (s[d] - x) * invM1;
+        ee += x * x; uu += u * u; eu += x * u;
+      }
+      ee = warp_sum(ee); uu = warp_sum(uu); eu = warp_sum(eu);
+      const float i_e = 1.0f / fmaxf(sqrtf(ee), kCosEps);
+      const float i_u = 1.0f / fmaxf(sqrtf(uu), kCosEps);
+      for (int d = lane; d < D; d += 32) rH[m * D + d] = e[d] * i_e;
+      if (lane == 0) { ine[m] = i_e; inu[m] = i_u; cosd[m] = eu * i_e * i_u; }
+    } else {
+      for (int d = lane; d < D; d += 32) rH[m * D + d] = 0.f;
+      if (lane == 0) { ine[m] = 0.f; inu[m] = 0.f; cosd[m] = 0.f; adiag[m] = 0.f; }
+    }
+  }
+  grid.sync();
+
+  // ------------------------------------------------------------------ phase 2
+  for (int i = tid; i < L.Npad * D4; i += kST) {
+    const int k = i / D4, d4 = i - k * D4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < N) v = __ldcg(reinterpret_cast<const float4*>(a.Chat + (size_t)k * D) + d4);
+    *reinterpret_cast<float4*>(Ch + (size_t)k * L.LDC + 4 * d4) = v;
+  }
+  __syncthreads();
+  {   // cos partials: lane <-> centroid, warp task <-> (32 centroids, slice of D)
+    const int chunk = (D4 + L.DS - 1) / L.DS;
+    for (int task = warp; task < L.KB * L.DS; task += kSW) {
+      const int kb = task % L.KB, ds = task / L.KB;
+      const int k = kb * 32 + lane;
+      const int kk = k < L.Npad ? k : L.Npad - 1;
+      float acc[MP];
+#pragma unroll
+      for (int m = 0; m < MP; ++m) acc[m] = 0.f;
+      const int d4e = (ds + 1) * chunk < D4 ? (ds + 1) * chunk : D4;
+      for (int d4 = ds * chunk; d4 < d4e; ++d4) {
+        const float4 c = *reinterpret_cast<const float4*>(Ch + (size_t)kk * L.LDC + 4 * d4);
+#pragma unroll
+        for (int m = 0; m < MP; ++m) {
+          const float4 e = *reinterpret_cast<const float4*>(rH + m * D + 4 * d4);
+          acc[m] = fmaf(c.x, e.x, acc[m]); acc[m] = fmaf(c.y, e.y, acc[m]);
+          acc[m] = fmaf(c.z, e.z, acc[m]); acc[m] = fmaf(c.w, e.w, acc[m]);
+        }
+      }
+      if (k < L.Npad) {
+#pragma unroll
+        for (int m = 0; m < MP; ++m) U[(ds * MP + m) * L.Npad + k] = acc[m];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < MP * L.Npad; i += kST) {
+    const int m = i / L.Npad, k = i - m * L.Npad;
+    float v = 0.f;
+    for (int ds = 0; ds < L.DS; ++ds) v += U[(ds * MP + m) * L.Npad + k];
+    if (k == j) v = cosd[m];                       // diagonal overwrite (utils.py:113)
+    cosr[i] = v;
+  }
+  __syncthreads();
+  {   // softmax: one warp per row
+    const float w = *a.w, b = *a.b;
+    for (int m = warp; m < M; m += kSW) {
+      const float* t = cosr + m * L.Npad;
+      const float cd = cosd[m];
+      float mx = -INFINITY;
+      for (int k = lane; k < N; k += 32) mx = fmaxf(mx, w * (t[k] + kCosBias) + b);
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int k = lane; k < N; k += 32) se += expf(w * (t[k] + kCosBias) + b - mx);
+      se = warp_sum(se);
+      const float tiny = kLogBias * expf(-mx);
+      const float den = se + tiny;
+      const float per = -(w * (cd + kCosBias) + b) + mx + logf(den);
+      const float inv_den = 1.0f / den;
+      float dwp = 0.f, ad = 0.f;
+      for (int k = lane; k < N; k += 32) {
+        const float c0 = t[k];
+        float g = expf(w * (c0 + kCosBias) + b - mx) * inv_den;
+        if (k == j) g -= 1.0f;
+        dwp += g * (c0 + kCosBias);
+        const float A = w * g;
+        if (k == j) ad = A;
+        At[k * MP + m] = (k == j) ? 0.f : A;
+      }
+      dwp = warp_sum(dwp); ad = warp_sum(ad);
+      if (lane == 0) {
+        const size_t row = row0 + m;
+        a.rowstat[row] = per;
+        a.rowstat[NM + row] = dwp;
+        a.rowstat[2 * NM + row] = -tiny * inv_den;
+        if (a.per_out) a.per_out[row] = per;
+        adiag[m] = ad;
+      }
+    }
+  }
+  __syncthreads();
+  if (a.need_grad) {
+    // R[m, d] = sum_k A_off[m, k] c^_k[d] (on chip) and this speaker's slab of P[k, d] = sum_m A_off[m, k] e^_m[d]
+    const int kc = (L.Npad + L.KH - 1) / L.KH;
+    float* slab = a.dC + (size_t)j * N * D;
+    for (int idx = tid; idx < D * L.KH; idx += kST) {
+      const int kh = idx / D, d = idx - kh * D;
+      const int k0 = kh * kc, k1 = (k0 + kc < L.Npad) ? k0 + kc : L.Npad;
+      float eh[MP], acc[MP];
+#pragma unroll
+      for (int m = 0; m < MP; ++m) { eh[m] = rH[m * D + d]; acc[m] = 0.f; }
+      for (int k = k0; k < k1; ++k) {
+        float at[MP];
+#pragma unroll
+        for (int m4 = 0; m4 < MP / 4; ++m4) {
+          const float4 v = *reinterpret_cast<const float4*>(At + k * MP + 4 * m4);
+          at[4 * m4] = v.x; at[4 * m4 + 1] = v.y; at[4 * m4 + 2] = v.z; at[4 * m4 + 3] = v.w;
+        }
+        const float c = Ch[(size_t)k * L.LDC + d];
+        float p = 0.f;
+#pragma unroll
+        for (int m = 0; m < MP; ++m) { acc[m] = fmaf(at[m], c, acc[m]); p = fmaf(at[m], eh[m], p); }
+        if (k < N) __stcg(slab + (size_t)k * D + d, p);
+      }
+#pragma unroll
+      for (int m = 0; m < MP; ++m) U[(kh * MP + m) * D + d] = acc[m];
+    }
+    __syncthreads();
+    for (int i = tid; i < MP * D; i += kST) {
+      float v = U[i];
+      for (int kh = 1; kh < L.KH; ++kh) v += U[kh * MP * D + i];
+      U[i] = v;                                     // rR = U[0 .. MP*D)
+    }
+  }
+  grid.sync();
+
+  // ------------------------------------------------------------------ phase 3
+  if (a.need_grad) {
+    const float* rR = U;
+    const float gs = a.gscale ? *a.gscale : 1.0f;
+    const int jc = (N + L.KH - 1) / L.KH;
+    for (int idx = tid; idx < D * L.KH; idx += kST) {
+      const int jh = idx / D, d = idx - jh * D;
+      const int j0 = jh * jc, j1 = (j0 + jc < N) ? j0 + jc : N;
+      const float* p = a.dC + ((size_t)j0 * N + j) * D + d;
+      const size_t st = (size_t)N * D;
+      float v = 0.f;
+      int jj = j0;
+      for (; jj + 8 <= j1; jj += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldcg(p + (size_t)u * st);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += t[u];
+        p += 8 * st;
+      }
+      for (; jj < j1; ++jj) { v += __ldcg(p); p += st; }
+      Pq[jh * D + d] = v;
+    }
+    __syncthreads();
+    float q = 0.f;
+    for (int d = tid; d < D; d += kST) {
+      float v = Pq[d];
+      for (int jh = 1; jh < L.KH; ++jh) v += Pq[jh * D + d];
+      Pv[d] = v;
+      q += v * Ch[(size_t)j * L.LDC + d];
+    }
+    q = block_sum_s(q, red);
+    for (int m = warp; m < M; m += kSW) {
+      float r = 0.f;
+      for (int d = lane; d < D; d += 32) r += rR[m * D + d] * rH[m * D + d];
+      r = warp_sum(r);
+      if (lane == 0) rr[m] = r;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < D * L.KH; idx += kST) {
+      const int mh = idx / D, d = idx - mh * D;
+      const float sj = s[d];
+      const float chd = Ch[(size_t)j * L.LDC + d];
+      float sumdu = 0.f;
+      for (int m = 0; m < M; ++m) {
+        const float eh = rH[m * D + d], i_u = inu[m];
+        const float uh = (sj - rE[m * D + d]) * invM1 * i_u;
+        sumdu += adiag[m] * (eh - cosd[m] * uh) * i_u;
+      }
+      const float dc = (Pv[d] - q * chd) * incj * invM;
+      for (int m = mh; m < M; m += L.KH) {
+        const float eh = rH[m * D + d];
+        const float i_e = ine[m], i_u = inu[m], cd = cosd[m], ad = adiag[m];
+        const float uh = (sj - rE[m * D + d]) * invM1 * i_u;
+        const float du = ad * (eh - cd * uh) * i_u;
+        const float local = (rR[m * D + d] - rr[m] * eh) * i_e + ad * (uh - cd * eh) * i_e;
+        a.dE[(row0 + m) * D + d] = gs * (local + dc + (sumdu - du) * invM1);
+      }
+    }
+  }
+  if (j == 0) {
+    const float gs = a.gscale ? *a.gscale : 1.0f;
+    float l = 0.f, dw = 0.f, db = 0.f;
+    for (int r = tid; r < NM; r += kST) {
+      l += __ldcg(a.rowstat + r); dw += __ldcg(a.rowstat + NM + r); db += __ldcg(a.rowstat + 2 * NM + r);
+    }
+    l = block_sum_s(l, red); dw = block_sum_s(dw, red); db = block_sum_s(db, red);
+    if (tid == 0) {
+      if (a.loss_out) *a.loss_out = l;
+      if (a.dw) *a.dw = gs * dw;
+      if (a.db) *a.db = gs * db;
+    }
+  }
+}
+
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+static bool spk_candidate(int N, int M, int D, int Nc) {
+  return Nc == N && M <= kSpkMaxM && D % 4 == 0 && N <= kSpkMaxN;
+}
+static int spk_mp(int M) { return M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : 16; }
 
 static size_t carve(Ge2eArgs& a, char* base) {
   const size_t NM = (size_t)a.N * a.M, D = a.D, Nc = a.Nc;
@@ -442,7 +755,7 @@ static size_t carve(Ge2eArgs& a, char* base) {
   auto take = [&](size_t nfloats) { float* p = base ? reinterpret_cast<float*>(base + off) : nullptr; off += align_up(nfloats * 4); return p; };
   a.Ehat = take(NM * D); a.Chat = take(Nc * D); a.Ssum = take((size_t)a.N * D);
   a.inv_ne = take(NM); a.inv_nu = take(NM); a.cosd = take(NM); a.inv_nc = take(Nc);
-  a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take((size_t)a.psplit * Nc * D); a.R = take(NM * D);
+  a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take((size_t)(spk_candidate(a.N, a.M, a.D, a.Nc) && a.N > a.psplit ? a.N : a.psplit) * Nc * D); a.R = take(NM * D);
   return off;
 }
 
@@ -505,6 +818,25 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   if (b1tiles > want) want = b1tiles;
   if (ctiles > want && a.need_grad) want = ctiles;
   if (b2blocks > want) want = b2blocks;
+  if (fused == 1 && spk_candidate(N, M, D, Nc) && !Cext && w && !dcos && !cos_out && N <= num_sms) {
+    // small batch (the reference's training batch): one CTA per speaker, three phases
+    const int MP = spk_mp(M);
+    const size_t sm = spk_layout(N, D, MP).floats * sizeof(float);
+    if (sm <= 220 * 1024) {
+      void* fn = MP == 4 ? (void*)ge2e_speaker_kernel<4> : MP == 8 ? (void*)ge2e_speaker_kernel<8>
+                 : MP == 12 ? (void*)ge2e_speaker_kernel<12> : (void*)ge2e_speaker_kernel<16>;
+      static int spk_smem_set[4] = {0, 0, 0, 0};
+      if ((int)sm > spk_smem_set[MP / 4 - 1]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute (speaker kernel)", e); return SVB_ERR_CUDA; }
+        spk_smem_set[MP / 4 - 1] = (int)sm;
+      }
+      void* params[] = {&a};
+      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(N), dim3(kST), params, sm, s);
+      if (e != cudaSuccess) { set_error("svb_ge2e: cooperative launch (speaker kernel)", e); return SVB_ERR_CUDA; }
+      return SVB_OK;
+    }
+  }
   if (fused) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, kThreads, smem);

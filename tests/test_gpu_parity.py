@@ -54,7 +54,7 @@ def net(svb):
 
 
 # ----------------------------------------------------------------------------------------------- GE2E
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [1, 2, 0])   # 1: per-speaker kernel (all cases are eligible), 2: general, 0: phases
 @pytest.mark.parametrize("name", list(I.GE2E_CASES))
 def test_ge2e_loss_and_gradients(svb, name, fused):
     N, M, D, kind, w0, b0 = I.GE2E_CASES[name]
@@ -75,6 +75,31 @@ def test_ge2e_loss_and_gradients(svb, name, fused):
     assert rel(E.grad.cpu().numpy(), o32["dE"]) < 1e-5
     assert rel(crit.w.grad.item(), g["dw_f64"]) < 1e-5
     assert rel(crit.b.grad.item(), g["db_f64"]) < 2e-3     # ill-conditioned; fp32 reference is ~2e-2 off
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 4), (33, 7, 20), (64, 10, 256), (100, 16, 256), (120, 13, 64), (37, 9, 512)])
+def test_ge2e_speaker_kernel_matches_general_kernel(svb, shape):
+    """The one-CTA-per-speaker kernel (small batches) against the general five-phase kernel and the fp64 oracle on
+    shapes that exercise its padding (N % 4, N % 32, M % 4, D < / > the block size)."""
+    N, M, D = shape
+    r = np.random.RandomState(N * 1000 + M)
+    Enp = (r.randn(N, 1, D) + 0.7 * r.randn(N, M, D)).astype(np.float32)
+    o = oge2e.ge2e_fwd_bwd(Enp.astype(np.float64), 10.0, -5.0)
+    res = []
+    for fused in (1, 2):
+        E = torch.tensor(Enp, device="cuda", requires_grad=True)
+        crit = svb.GE2ELoss("cuda")
+        crit.fused = fused
+        loss = crit(E)
+        loss.backward()
+        assert rel(loss.item(), o["loss"]) < 1e-5
+        assert rel(E.grad.cpu().numpy(), o["dE"]) < 1e-5
+        assert rel(crit.w.grad.item(), o["dw"]) < 1e-5
+        res.append((loss.item(), E.grad.clone()))
+    assert rel(res[0][0], res[1][0]) < 1e-6 and rel(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 1e-5
+    with torch.no_grad():                                   # forward-only mode of the speaker kernel
+        crit = svb.GE2ELoss("cuda")
+        assert rel(crit(torch.tensor(Enp, device="cuda")).item(), o["loss"]) < 1e-5
 
 
 def test_ge2e_upstream_scale_and_no_grad(svb):

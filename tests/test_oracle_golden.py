@@ -172,3 +172,21 @@ def test_dvector_windows_and_alignment():
         np.testing.assert_array_equal(out, g[f"align_W{W}"])
     sizes = [e - s for s, e in dvector.partitions(30)]
     assert sizes[:7] == [2, 3, 4, 3, 3, 4, 3]
+
+
+def test_optimizer_tail_closed_form_matches_library_calls():
+    """oracle.optim: the closed form the CUDA kernel follows vs. clip_grad_norm_ + torch.optim.SGD (the entry points
+    train_speech_embedder.py:63-65 calls), with a group that clips and one that does not."""
+    from oracle import optim as ooptim
+    r = np.random.RandomState(5)
+    g0 = [(r.randn(3072, 40).astype(np.float32), r.randn(3072, 40).astype(np.float32) * 0.5),
+          (r.randn(3072).astype(np.float32), r.randn(3072).astype(np.float32))]
+    g1 = [(np.float32(10.0).reshape(()), np.float32(0.3).reshape(())),
+          (np.float32(-5.0).reshape(()), np.float32(-0.2).reshape(()))]
+    groups = [(g0, 3.0), (g1, 1.0)]
+    pl, gl, nl = ooptim.clip_sgd_library(groups, 0.01)
+    pn, gn, nn_ = ooptim.clip_sgd_numpy(groups, 0.01)
+    assert nl[0] > 3.0 and nl[1] < 1.0
+    np.testing.assert_allclose(nl, nn_, rtol=1e-6)
+    for a, b in zip(sum(pl, []) + sum(gl, []), sum(pn, []) + sum(gn, [])):
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7)
