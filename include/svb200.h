@@ -95,7 +95,8 @@ int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);
  * Outputs (any may be NULL): cos_out (N,M,Nc) incl. the +1e-6 of utils.py:114; per_out (N,M) per-embedding loss;
  *   loss_out scalar (SUM, utils.py:131); dE (N,M,D); dCext (Nc,D); dw, db scalars.
  * fused = 1: single cooperative launch; loss batches with N <= #SMs, M <= 16, D % 4 == 0 (the reference's training
- *   batches) take the one-CTA-per-speaker kernel (3 phases, 2 grid barriers), everything else the general 5-phase
+ *   batches) take the per-speaker kernel (3 phases, 2 grid barriers; one 2-CTA cluster per speaker, each CTA owning
+ *   half of D, when D % 8 == 0 and 2N <= #SMs, else one CTA per speaker), everything else the general 5-phase
  *   kernel; fused = 2: always the general kernel; 0: one launch per phase (debug). */
 int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w, const float* b,
              const float* dcos, const float* gscale, float* cos_out, float* per_out, float* loss_out, float* dE,

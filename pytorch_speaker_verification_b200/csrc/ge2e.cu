@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -61,6 +62,7 @@ struct Ge2eArgs {
   float* rowstat;        // [3, N*M]: per-row loss, dw, db contributions
   float* dC;             // [Nc, D]  P = A_off^T E^ (numerator of the centroid gradient)
   float* R;              // [N*M, D] A_off C^
+  long long* trace;      // debug (SVB_GE2E_TRACE=1): [N, 16] clock64 stamps of the per-speaker kernel, else null
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -429,14 +431,17 @@ __global__ void __launch_bounds__(kThreads) ge2e_phase_kernel(const Ge2eArgs a, 
 }
 
 // ---------------------------------------------------------------------------------------------- small-batch kernel
-// One CTA per speaker, three phases, two grid barriers (the training batch of the reference, N = 64 x M = 10, is far
-// too small for five phases of tiled GEMMs: the general kernel above spends its time in barriers and L2 round trips).
-//   1  CTA j: its M rows -> utterance sum, unit centroid c^_j (published: N x D floats is all the other CTAs need),
-//      per-row norms, leave-one-out cosine, e^ (kept in shared memory for the whole kernel)
-//   2  CTA j: all unit centroids -> shared memory; cos for its M rows, softmax, A = wG; R = A_off C^ stays on chip;
-//      its contribution to every centroid's P_k = sum_rows A_off e^ goes to a [j][k][D] slab (fixed-order sum later)
-//   3  CTA k: P_k = sum_j slab[j][k], dC_k, and dE of its own rows (everything else is still in shared memory)
-// Eligibility (svb_ge2e, fused == 1): own centroids, loss mode, M <= 16, D % 4 == 0, N <= #SMs, shared memory fits.
+// One CTA (CL = 1) or one 2-CTA cluster (CL = 2, each CTA owning half of the D embedding dimensions) per speaker,
+// three phases, two grid barriers.  The training batch of the reference (N = 64 x M = 10) is far too small for five
+// phases of tiled GEMMs: the general kernel above spends its time in barriers and L2 round trips.
+//   1  speaker j: its M rows -> utterance sum, unit centroid c^_j (published: N x D floats is all the other speakers
+//      need), per-row norms, leave-one-out cosine, e^ (kept in shared memory for the whole kernel)
+//   2  speaker j: all unit centroids -> shared memory; cos for its M rows, softmax, A = wG; R = A_off C^ stays on
+//      chip; its contribution to every centroid's P_k = sum_rows A_off e^ goes to a [j][k][D] slab
+//   3  speaker k: P_k = sum_j slab[j][k] (fixed order), dC_k, and dE of its own rows (the rest is still on chip)
+// With CL = 2 every full-D dot product (row norms, cos, q, r) is the sum of the two CTAs' partial sums, exchanged
+// through distributed shared memory and added in rank order by both, so the two halves see identical scalars.
+// Eligibility (svb_ge2e, fused == 1): own centroids, loss mode, M <= 16, D % 4 == 0, CL * N <= #SMs.
 constexpr int kST = 512;
 constexpr int kSW = kST / 32;
 constexpr int kSpkMaxN = 148;
@@ -454,109 +459,149 @@ __device__ float block_sum_s(float v, float* red) {
 }
 
 struct SpkLayout {
-  int Npad, LDC, KB, DS, KH, U;   // U = floats of the aliased scratch region
+  int Npad, LDC, KB, DS, KH, U, XB;   // U = floats of the aliased scratch region, XB = floats of one exchange slot
   size_t floats;
 };
-__host__ __device__ inline SpkLayout spk_layout(int N, int D, int MP) {
+// DH = embedding dimensions owned by one CTA (D / CL), MP = compute rows (M rounded up to even)
+__host__ __device__ inline SpkLayout spk_layout(int N, int DH, int MP) {
   SpkLayout l;
+  const int MS = (MP + 3) & ~3;
   l.Npad = (N + 3) & ~3;
-  l.LDC = D + 4;
+  l.LDC = DH + 4;
   l.KB = (N + 31) / 32;
   int ds = kSW / l.KB;
   if (ds < 1) ds = 1;
-  if (ds > D / 4) ds = D / 4;
+  if (ds > DH / 4) ds = DH / 4;
   l.DS = ds;
-  l.KH = D >= kST ? 1 : kST / D;
+  l.KH = DH >= kST ? 1 : kST / DH;
   const int u1 = l.DS * MP * l.Npad;
-  const int u2 = l.KH * MP * D;
+  const int u2 = l.KH * MP * DH;
   l.U = u1 > u2 ? u1 : u2;
-  l.floats = (size_t)l.Npad * l.LDC     // Ch
-             + 2 * (size_t)MP * D       // rE, rH
-             + (size_t)l.U              // cos partials | R partials
-             + 2 * (size_t)MP * l.Npad  // cosr, At
-             + 2 * (size_t)D            // s, Pv
-             + (size_t)(l.KH * D)       // Pq
-             + 5 * (size_t)MP + 32;     // ine, inu, cosd, adiag, rr, red
+  l.XB = 3 * MS + 4;
+  l.floats = (size_t)l.Npad * l.LDC          // Ch
+             + 2 * (size_t)MS * DH           // rE, rH
+             + (size_t)l.U                   // cos partials | R partials
+             + 3 * (size_t)MS * l.Npad       // cosr, xcos[2]
+             + (size_t)l.Npad * MS           // At
+             + 2 * (size_t)DH                // s, Pv
+             + (size_t)(l.KH * DH)           // Pq
+             + 2 * (size_t)l.XB              // xb[2]
+             + 5 * (size_t)MS + 32;          // ine, inu, cosd, adiag, rr, red
   return l;
 }
 
-template <int MP>
+template <int MP, int CL>
 __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) {
+  constexpr int MS = (MP + 3) & ~3;       // row stride of the [k][m] arrays (float4 loads)
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   cg::grid_group grid = cg::this_grid();
-  const int N = a.N, M = a.M, D = a.D, NM = N * M, D4 = D / 4;
-  const SpkLayout L = spk_layout(N, D, MP);
+  const int N = a.N, M = a.M, D = a.D, NM = N * M;
+  const int h = CL > 1 ? (int)(blockIdx.x % CL) : 0;           // rank in the cluster = which slice of D
+  const int j = blockIdx.x / CL;
+  const int DH = D / CL, d0 = h * DH, DH4 = DH / 4;
+  const SpkLayout L = spk_layout(N, DH, MP);
   float* Ch = smem;
   float* rE = Ch + (size_t)L.Npad * L.LDC;
-  float* rH = rE + MP * D;
-  float* U = rH + MP * D;
+  float* rH = rE + MS * DH;
+  float* U = rH + MS * DH;
   float* cosr = U + L.U;
-  float* At = cosr + MP * L.Npad;
-  float* s = At + MP * L.Npad;
-  float* Pv = s + D;
-  float* Pq = Pv + D;
-  float* ine = Pq + L.KH * D;
-  float* inu = ine + MP;
-  float* cosd = inu + MP;
-  float* adiag = cosd + MP;
-  float* rr = adiag + MP;
-  float* red = rr + MP;
+  float* xcos = cosr + MS * L.Npad;       // [2][MS * Npad]
+  float* At = xcos + 2 * MS * L.Npad;     // [Npad][MS]
+  float* s = At + L.Npad * MS;
+  float* Pv = s + DH;
+  float* Pq = Pv + DH;
+  float* xb = Pq + L.KH * DH;             // [2][XB]
+  float* ine = xb + 2 * L.XB;
+  float* inu = ine + MS;
+  float* cosd = inu + MS;
+  float* adiag = cosd + MS;
+  float* rr = adiag + MS;
+  float* red = rr + MS;
+  float* xb_peer = xb;
+  float* xcos_peer = xcos;
+  if constexpr (CL > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    xb_peer = cluster.map_shared_rank(xb, h ^ 1);
+    xcos_peer = cluster.map_shared_rank(xcos, h ^ 1);
+  }
+  auto exchange_sync = [&]() {
+    if constexpr (CL > 1) cg::this_cluster().sync(); else __syncthreads();
+  };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int j = blockIdx.x;
   const size_t row0 = (size_t)j * M;
   const float invM = 1.0f / (float)M, invM1 = 1.0f / (float)(M - 1);
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 0] = clock64();
 
   // ------------------------------------------------------------------ phase 1
   {
-    const float4* Ej = reinterpret_cast<const float4*>(a.E + row0 * D);
     float4* rE4 = reinterpret_cast<float4*>(rE);
-    for (int i = tid; i < MP * D4; i += kST) rE4[i] = (i < M * D4) ? Ej[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < MP * L.Npad; i += kST) At[i] = 0.f;
+    for (int i = tid; i < MP * DH4; i += kST) {
+      const int m = i / DH4, d4 = i - m * DH4;
+      rE4[i] = (m < M) ? __ldg(reinterpret_cast<const float4*>(a.E + (row0 + m) * D + d0) + d4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < L.Npad * MS; i += kST) At[i] = 0.f;
   }
   __syncthreads();
   float cc = 0.f;
-  for (int d = tid; d < D; d += kST) {
+  for (int d = tid; d < DH; d += kST) {
     float acc = 0.f;
-    for (int m = 0; m < M; ++m) acc += rE[m * D + d];
+    for (int m = 0; m < M; ++m) acc += rE[m * DH + d];
     s[d] = acc;
     const float c = acc * invM;
     cc += c * c;
   }
   cc = block_sum_s(cc, red);
+  if (tid == 0) { xb[h * L.XB + 3 * MS] = cc; if (CL > 1) xb_peer[h * L.XB + 3 * MS] = cc; }
+  for (int m = warp; m < M; m += kSW) {
+    const float* e = rE + m * DH;
+    float ee = 0.f, uu = 0.f, eu = 0.f;
+    for (int d = lane; d < DH; d += 32) {
+      const float x = e[d];
+      const float u = (s[d] - x) * invM1;
+      ee += x * x; uu += u * u; eu += x * u;
+    }
+    ee = warp_sum(ee); uu = warp_sum(uu); eu = warp_sum(eu);
+    if (lane == 0) {
+      float* o = xb + h * L.XB + 3 * m;
+      o[0] = ee; o[1] = uu; o[2] = eu;
+      if (CL > 1) { float* p = xb_peer + h * L.XB + 3 * m; p[0] = ee; p[1] = uu; p[2] = eu; }
+    }
+  }
+  exchange_sync();
+  cc = xb[3 * MS];
+  if (CL > 1) cc += xb[L.XB + 3 * MS];
   const float incj = 1.0f / fmaxf(sqrtf(cc), kCosEps);
-  for (int d = tid; d < D; d += kST) a.Chat[(size_t)j * D + d] = s[d] * invM * incj;
+  for (int d = tid; d < DH; d += kST) a.Chat[(size_t)j * D + d0 + d] = s[d] * invM * incj;
   for (int m = warp; m < MP; m += kSW) {
     if (m < M) {
-      const float* e = rE + m * D;
-      float ee = 0.f, uu = 0.f, eu = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        const float x = e[d];
-        const float u = (s[d] - x) * invM1;
-        ee += x * x; uu += u * u; eu += x * u;
-      }
-      ee = warp_sum(ee); uu = warp_sum(uu); eu = warp_sum(eu);
+      float ee = xb[3 * m], uu = xb[3 * m + 1], eu = xb[3 * m + 2];
+      if (CL > 1) { ee += xb[L.XB + 3 * m]; uu += xb[L.XB + 3 * m + 1]; eu += xb[L.XB + 3 * m + 2]; }
       const float i_e = 1.0f / fmaxf(sqrtf(ee), kCosEps);
       const float i_u = 1.0f / fmaxf(sqrtf(uu), kCosEps);
-      for (int d = lane; d < D; d += 32) rH[m * D + d] = e[d] * i_e;
+      for (int d = lane; d < DH; d += 32) rH[m * DH + d] = rE[m * DH + d] * i_e;
       if (lane == 0) { ine[m] = i_e; inu[m] = i_u; cosd[m] = eu * i_e * i_u; }
     } else {
-      for (int d = lane; d < D; d += 32) rH[m * D + d] = 0.f;
+      for (int d = lane; d < DH; d += 32) rH[m * DH + d] = 0.f;
       if (lane == 0) { ine[m] = 0.f; inu[m] = 0.f; cosd[m] = 0.f; adiag[m] = 0.f; }
     }
   }
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 1] = clock64();
   grid.sync();
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 2] = clock64();
 
   // ------------------------------------------------------------------ phase 2
-  for (int i = tid; i < L.Npad * D4; i += kST) {
-    const int k = i / D4, d4 = i - k * D4;
+  for (int i = tid; i < L.Npad * DH4; i += kST) {
+    const int k = i / DH4, d4 = i - k * DH4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < N) v = __ldcg(reinterpret_cast<const float4*>(a.Chat + (size_t)k * D) + d4);
+    if (k < N) v = __ldcg(reinterpret_cast<const float4*>(a.Chat + (size_t)k * D + d0) + d4);
     *reinterpret_cast<float4*>(Ch + (size_t)k * L.LDC + 4 * d4) = v;
   }
   __syncthreads();
-  {   // cos partials: lane <-> centroid, warp task <-> (32 centroids, slice of D)
-    const int chunk = (D4 + L.DS - 1) / L.DS;
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 3] = clock64();
+  {   // cos partials: lane <-> centroid, warp task <-> (32 centroids, slice of the CTA's dimensions)
+    const int chunk = (DH4 + L.DS - 1) / L.DS;
     for (int task = warp; task < L.KB * L.DS; task += kSW) {
       const int kb = task % L.KB, ds = task / L.KB;
       const int k = kb * 32 + lane;
@@ -564,12 +609,12 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
       float acc[MP];
 #pragma unroll
       for (int m = 0; m < MP; ++m) acc[m] = 0.f;
-      const int d4e = (ds + 1) * chunk < D4 ? (ds + 1) * chunk : D4;
+      const int d4e = (ds + 1) * chunk < DH4 ? (ds + 1) * chunk : DH4;
       for (int d4 = ds * chunk; d4 < d4e; ++d4) {
         const float4 c = *reinterpret_cast<const float4*>(Ch + (size_t)kk * L.LDC + 4 * d4);
 #pragma unroll
         for (int m = 0; m < MP; ++m) {
-          const float4 e = *reinterpret_cast<const float4*>(rH + m * D + 4 * d4);
+          const float4 e = *reinterpret_cast<const float4*>(rH + m * DH + 4 * d4);
           acc[m] = fmaf(c.x, e.x, acc[m]); acc[m] = fmaf(c.y, e.y, acc[m]);
           acc[m] = fmaf(c.z, e.z, acc[m]); acc[m] = fmaf(c.w, e.w, acc[m]);
         }
@@ -582,23 +627,26 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
   }
   __syncthreads();
   for (int i = tid; i < MP * L.Npad; i += kST) {
-    const int m = i / L.Npad, k = i - m * L.Npad;
     float v = 0.f;
-    for (int ds = 0; ds < L.DS; ++ds) v += U[(ds * MP + m) * L.Npad + k];
-    if (k == j) v = cosd[m];                       // diagonal overwrite (utils.py:113)
-    cosr[i] = v;
+    for (int ds = 0; ds < L.DS; ++ds) v += U[ds * MP * L.Npad + i];
+    if (CL > 1) { xcos[h * MS * L.Npad + i] = v; xcos_peer[h * MS * L.Npad + i] = v; } else cosr[i] = v;
   }
-  __syncthreads();
-  {   // softmax: one warp per row
+  exchange_sync();
+  if (CL > 1) {
+    for (int i = tid; i < MP * L.Npad; i += kST) cosr[i] = xcos[i] + xcos[MS * L.Npad + i];
+    __syncthreads();
+  }
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 4] = clock64();
+  {   // softmax: one warp per row (both CTAs of a cluster, identical inputs -> identical A)
     const float w = *a.w, b = *a.b;
     for (int m = warp; m < M; m += kSW) {
       const float* t = cosr + m * L.Npad;
       const float cd = cosd[m];
       float mx = -INFINITY;
-      for (int k = lane; k < N; k += 32) mx = fmaxf(mx, w * (t[k] + kCosBias) + b);
+      for (int k = lane; k < N; k += 32) mx = fmaxf(mx, w * ((k == j ? cd : t[k]) + kCosBias) + b);   // utils.py:113
       mx = warp_max(mx);
       float se = 0.f;
-      for (int k = lane; k < N; k += 32) se += expf(w * (t[k] + kCosBias) + b - mx);
+      for (int k = lane; k < N; k += 32) se += expf(w * ((k == j ? cd : t[k]) + kCosBias) + b - mx);
       se = warp_sum(se);
       const float tiny = kLogBias * expf(-mx);
       const float den = se + tiny;
@@ -606,70 +654,79 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
       const float inv_den = 1.0f / den;
       float dwp = 0.f, ad = 0.f;
       for (int k = lane; k < N; k += 32) {
-        const float c0 = t[k];
+        const float c0 = (k == j) ? cd : t[k];
         float g = expf(w * (c0 + kCosBias) + b - mx) * inv_den;
         if (k == j) g -= 1.0f;
         dwp += g * (c0 + kCosBias);
         const float A = w * g;
         if (k == j) ad = A;
-        At[k * MP + m] = (k == j) ? 0.f : A;
+        At[k * MS + m] = (k == j) ? 0.f : A;
       }
       dwp = warp_sum(dwp); ad = warp_sum(ad);
       if (lane == 0) {
-        const size_t row = row0 + m;
-        a.rowstat[row] = per;
-        a.rowstat[NM + row] = dwp;
-        a.rowstat[2 * NM + row] = -tiny * inv_den;
-        if (a.per_out) a.per_out[row] = per;
+        if (h == 0) {
+          const size_t row = row0 + m;
+          a.rowstat[row] = per;
+          a.rowstat[NM + row] = dwp;
+          a.rowstat[2 * NM + row] = -tiny * inv_den;
+          if (a.per_out) a.per_out[row] = per;
+        }
         adiag[m] = ad;
       }
     }
   }
   __syncthreads();
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 5] = clock64();
   if (a.need_grad) {
     // R[m, d] = sum_k A_off[m, k] c^_k[d] (on chip) and this speaker's slab of P[k, d] = sum_m A_off[m, k] e^_m[d]
     const int kc = (L.Npad + L.KH - 1) / L.KH;
-    float* slab = a.dC + (size_t)j * N * D;
-    for (int idx = tid; idx < D * L.KH; idx += kST) {
-      const int kh = idx / D, d = idx - kh * D;
+    float* slab = a.dC + (size_t)j * N * D + d0;
+    for (int idx = tid; idx < DH * L.KH; idx += kST) {
+      const int kh = idx / DH, d = idx - kh * DH;
       const int k0 = kh * kc, k1 = (k0 + kc < L.Npad) ? k0 + kc : L.Npad;
       float eh[MP], acc[MP];
 #pragma unroll
-      for (int m = 0; m < MP; ++m) { eh[m] = rH[m * D + d]; acc[m] = 0.f; }
-      for (int k = k0; k < k1; ++k) {
-        float at[MP];
+      for (int m = 0; m < MP; ++m) { eh[m] = rH[m * DH + d]; acc[m] = 0.f; }
+      float* sp = slab + (size_t)k0 * D + d;
+      for (int k = k0; k < k1; ++k, sp += D) {
+        float at[MS];
 #pragma unroll
-        for (int m4 = 0; m4 < MP / 4; ++m4) {
-          const float4 v = *reinterpret_cast<const float4*>(At + k * MP + 4 * m4);
+        for (int m4 = 0; m4 < MS / 4; ++m4) {
+          const float4 v = *reinterpret_cast<const float4*>(At + k * MS + 4 * m4);
           at[4 * m4] = v.x; at[4 * m4 + 1] = v.y; at[4 * m4 + 2] = v.z; at[4 * m4 + 3] = v.w;
         }
         const float c = Ch[(size_t)k * L.LDC + d];
-        float p = 0.f;
+        float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-        for (int m = 0; m < MP; ++m) { acc[m] = fmaf(at[m], c, acc[m]); p = fmaf(at[m], eh[m], p); }
-        if (k < N) __stcg(slab + (size_t)k * D + d, p);
+        for (int m = 0; m < MP; m += 2) {
+          acc[m] = fmaf(at[m], c, acc[m]); acc[m + 1] = fmaf(at[m + 1], c, acc[m + 1]);
+          p0 = fmaf(at[m], eh[m], p0); p1 = fmaf(at[m + 1], eh[m + 1], p1);
+        }
+        if (k < N) __stcg(sp, p0 + p1);
       }
 #pragma unroll
-      for (int m = 0; m < MP; ++m) U[(kh * MP + m) * D + d] = acc[m];
+      for (int m = 0; m < MP; ++m) U[(kh * MP + m) * DH + d] = acc[m];
     }
     __syncthreads();
-    for (int i = tid; i < MP * D; i += kST) {
+    for (int i = tid; i < MP * DH; i += kST) {
       float v = U[i];
-      for (int kh = 1; kh < L.KH; ++kh) v += U[kh * MP * D + i];
-      U[i] = v;                                     // rR = U[0 .. MP*D)
+      for (int kh = 1; kh < L.KH; ++kh) v += U[kh * MP * DH + i];
+      U[i] = v;                                     // rR = U[0 .. MP*DH)
     }
   }
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 6] = clock64();
   grid.sync();
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 7] = clock64();
 
   // ------------------------------------------------------------------ phase 3
   if (a.need_grad) {
     const float* rR = U;
     const float gs = a.gscale ? *a.gscale : 1.0f;
     const int jc = (N + L.KH - 1) / L.KH;
-    for (int idx = tid; idx < D * L.KH; idx += kST) {
-      const int jh = idx / D, d = idx - jh * D;
+    for (int idx = tid; idx < DH * L.KH; idx += kST) {
+      const int jh = idx / DH, d = idx - jh * DH;
       const int j0 = jh * jc, j1 = (j0 + jc < N) ? j0 + jc : N;
-      const float* p = a.dC + ((size_t)j0 * N + j) * D + d;
+      const float* p = a.dC + ((size_t)j0 * N + j) * D + d0 + d;
       const size_t st = (size_t)N * D;
       float v = 0.f;
       int jj = j0;
@@ -682,46 +739,53 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
         p += 8 * st;
       }
       for (; jj < j1; ++jj) { v += __ldcg(p); p += st; }
-      Pq[jh * D + d] = v;
+      Pq[jh * DH + d] = v;
     }
     __syncthreads();
+    if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 8] = clock64();
     float q = 0.f;
-    for (int d = tid; d < D; d += kST) {
+    for (int d = tid; d < DH; d += kST) {
       float v = Pq[d];
-      for (int jh = 1; jh < L.KH; ++jh) v += Pq[jh * D + d];
+      for (int jh = 1; jh < L.KH; ++jh) v += Pq[jh * DH + d];
       Pv[d] = v;
       q += v * Ch[(size_t)j * L.LDC + d];
     }
     q = block_sum_s(q, red);
+    if (tid == 0) { xb[h * L.XB + 3 * MS] = q; if (CL > 1) xb_peer[h * L.XB + 3 * MS] = q; }
     for (int m = warp; m < M; m += kSW) {
       float r = 0.f;
-      for (int d = lane; d < D; d += 32) r += rR[m * D + d] * rH[m * D + d];
+      for (int d = lane; d < DH; d += 32) r += rR[m * DH + d] * rH[m * DH + d];
       r = warp_sum(r);
-      if (lane == 0) rr[m] = r;
+      if (lane == 0) { xb[h * L.XB + m] = r; if (CL > 1) xb_peer[h * L.XB + m] = r; }
     }
+    exchange_sync();
+    q = xb[3 * MS];
+    if (CL > 1) q += xb[L.XB + 3 * MS];
+    if (tid < M) rr[tid] = CL > 1 ? xb[tid] + xb[L.XB + tid] : xb[tid];
     __syncthreads();
-    for (int idx = tid; idx < D * L.KH; idx += kST) {
-      const int mh = idx / D, d = idx - mh * D;
+    for (int idx = tid; idx < DH * L.KH; idx += kST) {
+      const int mh = idx / DH, d = idx - mh * DH;
       const float sj = s[d];
       const float chd = Ch[(size_t)j * L.LDC + d];
       float sumdu = 0.f;
       for (int m = 0; m < M; ++m) {
-        const float eh = rH[m * D + d], i_u = inu[m];
-        const float uh = (sj - rE[m * D + d]) * invM1 * i_u;
+        const float eh = rH[m * DH + d], i_u = inu[m];
+        const float uh = (sj - rE[m * DH + d]) * invM1 * i_u;
         sumdu += adiag[m] * (eh - cosd[m] * uh) * i_u;
       }
       const float dc = (Pv[d] - q * chd) * incj * invM;
       for (int m = mh; m < M; m += L.KH) {
-        const float eh = rH[m * D + d];
+        const float eh = rH[m * DH + d];
         const float i_e = ine[m], i_u = inu[m], cd = cosd[m], ad = adiag[m];
-        const float uh = (sj - rE[m * D + d]) * invM1 * i_u;
+        const float uh = (sj - rE[m * DH + d]) * invM1 * i_u;
         const float du = ad * (eh - cd * uh) * i_u;
-        const float local = (rR[m * D + d] - rr[m] * eh) * i_e + ad * (uh - cd * eh) * i_e;
-        a.dE[(row0 + m) * D + d] = gs * (local + dc + (sumdu - du) * invM1);
+        const float local = (rR[m * DH + d] - rr[m] * eh) * i_e + ad * (uh - cd * eh) * i_e;
+        a.dE[(row0 + m) * D + d0 + d] = gs * (local + dc + (sumdu - du) * invM1);
       }
     }
   }
-  if (j == 0) {
+  if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 9] = clock64();
+  if (blockIdx.x == 0) {
     const float gs = a.gscale ? *a.gscale : 1.0f;
     float l = 0.f, dw = 0.f, db = 0.f;
     for (int r = tid; r < NM; r += kST) {
@@ -741,7 +805,20 @@ static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 static bool spk_candidate(int N, int M, int D, int Nc) {
   return Nc == N && M <= kSpkMaxM && D % 4 == 0 && N <= kSpkMaxN;
 }
-static int spk_mp(int M) { return M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : 16; }
+template <int CL>
+static void* spk_kernel_cl(int MP) {
+  switch (MP) {
+    case 2: return (void*)ge2e_speaker_kernel<2, CL>;
+    case 4: return (void*)ge2e_speaker_kernel<4, CL>;
+    case 6: return (void*)ge2e_speaker_kernel<6, CL>;
+    case 8: return (void*)ge2e_speaker_kernel<8, CL>;
+    case 10: return (void*)ge2e_speaker_kernel<10, CL>;
+    case 12: return (void*)ge2e_speaker_kernel<12, CL>;
+    case 14: return (void*)ge2e_speaker_kernel<14, CL>;
+    default: return (void*)ge2e_speaker_kernel<16, CL>;
+  }
+}
+static void* spk_kernel(int MP, int CL) { return CL > 1 ? spk_kernel_cl<2>(MP) : spk_kernel_cl<1>(MP); }
 
 static size_t carve(Ge2eArgs& a, char* base) {
   const size_t NM = (size_t)a.N * a.M, D = a.D, Nc = a.Nc;
@@ -756,6 +833,7 @@ static size_t carve(Ge2eArgs& a, char* base) {
   a.Ehat = take(NM * D); a.Chat = take(Nc * D); a.Ssum = take((size_t)a.N * D);
   a.inv_ne = take(NM); a.inv_nu = take(NM); a.cosd = take(NM); a.inv_nc = take(Nc);
   a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take((size_t)(spk_candidate(a.N, a.M, a.D, a.Nc) && a.N > a.psplit ? a.N : a.psplit) * Nc * D); a.R = take(NM * D);
+  a.trace = reinterpret_cast<long long*>(take(2 * 16 * (size_t)kSpkMaxN));
   return off;
 }
 
@@ -780,6 +858,16 @@ extern "C" int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* byt
   return SVB_OK;
 }
 
+// Debug: byte offset of the clock64 trace ([N, 16] int64) inside the workspace (written when SVB_GE2E_TRACE is set).
+extern "C" int svb_ge2e_trace_offset(int N, int M, int D, int Nc, size_t* offset) {
+  if (!offset) return SVB_ERR_ARG;
+  Ge2eArgs a{};
+  a.N = N; a.M = M; a.D = D; a.Nc = Nc;
+  const size_t total = carve(a, nullptr);
+  *offset = total - align_up(2 * 16 * (size_t)kSpkMaxN * 4);
+  return SVB_OK;
+}
+
 extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w,
                         const float* b, const float* dcos, const float* gscale, float* cos_out, float* per_out,
                         float* loss_out, float* dE, float* dCext, float* dw, float* db, void* workspace,
@@ -794,6 +882,8 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   if (a.need_grad && !w && !dcos) { set_error("svb_ge2e: gradient requested without w/b or dcos", cudaSuccess); return SVB_ERR_ARG; }
   a.cos_out = cos_out; a.per_out = per_out; a.loss_out = loss_out; a.dE = dE; a.dCext = dCext; a.dw = dw; a.db = db;
   if (carve(a, static_cast<char*>(workspace)) > workspace_bytes) { set_error("svb_ge2e: workspace too small", cudaSuccess); return SVB_ERR_ARG; }
+  static const bool trace_on = getenv("SVB_GE2E_TRACE") != nullptr;
+  if (!trace_on) a.trace = nullptr;
   const size_t smem = smem_bytes(a);
   if (smem > 200 * 1024) { set_error("svb_ge2e: M*D too large for one CTA's shared memory", cudaSuccess); return SVB_ERR_UNSUPPORTED; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -819,22 +909,32 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   if (ctiles > want && a.need_grad) want = ctiles;
   if (b2blocks > want) want = b2blocks;
   if (fused == 1 && spk_candidate(N, M, D, Nc) && !Cext && w && !dcos && !cos_out && N <= num_sms) {
-    // small batch (the reference's training batch): one CTA per speaker, three phases
-    const int MP = spk_mp(M);
-    const size_t sm = spk_layout(N, D, MP).floats * sizeof(float);
-    if (sm <= 220 * 1024) {
-      void* fn = MP == 4 ? (void*)ge2e_speaker_kernel<4> : MP == 8 ? (void*)ge2e_speaker_kernel<8>
-                 : MP == 12 ? (void*)ge2e_speaker_kernel<12> : (void*)ge2e_speaker_kernel<16>;
-      static int spk_smem_set[4] = {0, 0, 0, 0};
-      if ((int)sm > spk_smem_set[MP / 4 - 1]) {
+    // small batch (the reference's training batch): one CTA or one 2-CTA cluster per speaker, three phases
+    static int cluster_ok = 1;                       // cleared if the cooperative + cluster launch is refused
+    const int MP = (M + 1) & ~1;
+    for (int CL = (cluster_ok && D % 8 == 0 && 2 * N <= num_sms) ? 2 : 1; CL >= 1; --CL) {
+      const size_t sm = spk_layout(N, D / CL, MP).floats * sizeof(float);
+      if (sm > 220 * 1024) break;
+      void* fn = spk_kernel(MP, CL);
+      static int spk_smem_set[2][kSpkMaxM / 2] = {};
+      if ((int)sm > spk_smem_set[CL - 1][MP / 2 - 1]) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute (speaker kernel)", e); return SVB_ERR_CUDA; }
-        spk_smem_set[MP / 4 - 1] = (int)sm;
+        spk_smem_set[CL - 1][MP / 2 - 1] = (int)sm;
       }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(kST); cfg.dynamicSmemBytes = sm; cfg.stream = s;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+      at[1].id = cudaLaunchAttributeClusterDimension;
+      at[1].val.clusterDim.x = CL; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = CL > 1 ? 2 : 1;
       void* params[] = {&a};
-      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(N), dim3(kST), params, sm, s);
-      if (e != cudaSuccess) { set_error("svb_ge2e: cooperative launch (speaker kernel)", e); return SVB_ERR_CUDA; }
-      return SVB_OK;
+      cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
+      if (e == cudaSuccess) return SVB_OK;
+      if (CL == 1) { set_error("svb_ge2e: cooperative launch (speaker kernel)", e); return SVB_ERR_CUDA; }
+      cudaGetLastError();                            // cluster form refused: remember, take the single-CTA form
+      cluster_ok = 0;
     }
   }
   if (fused) {

@@ -77,10 +77,12 @@ def test_ge2e_loss_and_gradients(svb, name, fused):
     assert rel(crit.b.grad.item(), g["db_f64"]) < 2e-3     # ill-conditioned; fp32 reference is ~2e-2 off
 
 
-@pytest.mark.parametrize("shape", [(3, 2, 4), (33, 7, 20), (64, 10, 256), (100, 16, 256), (120, 13, 64), (37, 9, 512)])
+@pytest.mark.parametrize("shape", [(3, 2, 4), (33, 7, 20), (20, 5, 24), (64, 10, 256), (70, 10, 256), (100, 16, 256), (120, 13, 64),
+                                   (37, 9, 512), (74, 2, 8)])
 def test_ge2e_speaker_kernel_matches_general_kernel(svb, shape):
     """The one-CTA-per-speaker kernel (small batches) against the general five-phase kernel and the fp64 oracle on
-    shapes that exercise its padding (N % 4, N % 32, M % 4, D < / > the block size)."""
+    shapes that exercise its padding (N % 4, N % 32, odd M, D < / > the block size) in both forms: 2-CTA clusters
+    splitting D (D % 8 == 0 and 2N <= #SMs) and single CTAs."""
     N, M, D = shape
     r = np.random.RandomState(N * 1000 + M)
     Enp = (r.randn(N, 1, D) + 0.7 * r.randn(N, M, D)).astype(np.float32)
@@ -413,3 +415,44 @@ def test_state_dict_roundtrip_and_cpu_module(svb):
         e2 = e_gpu_module(x.cuda()).cpu()
     assert e_cpu_module.device.type == "cpu"
     assert torch.equal(e_cpu_module, e2)
+
+
+# ----------------------------------------------------------------------------------------------- optimizer tail
+def test_fused_clip_sgd_matches_clip_grad_norm_and_sgd(svb, net):
+    """svb.FusedClipSGD (csrc/optim.cu) against the torch entry points train_speech_embedder.py:63-65 calls
+    (oracle.optim.clip_sgd_library): updated parameters, clipped gradients and the returned norms."""
+    from oracle import optim as ooptim
+    import copy
+    r = np.random.RandomState(3)
+    m = copy.deepcopy(net)
+    crit = svb.GE2ELoss("cuda")
+    groups = []
+    for params, mn, gscale in ((list(m.parameters()), 3.0, 0.02), (list(crit.parameters()), 1.0, 0.1)):
+        pg = []
+        for p in params:
+            g = np.asarray(r.randn(*p.shape) * gscale, dtype=np.float32)
+            p.grad = torch.tensor(g, device="cuda").reshape(p.shape)
+            pg.append((p.detach().cpu().numpy().copy(), g))
+        groups.append((pg, mn))
+    versions = [p._version for p in m.parameters()]
+    opt = svb.FusedClipSGD([{"params": m.parameters(), "max_norm": 3.0}, {"params": crit.parameters(), "max_norm": 1.0}],
+                           lr=0.01)
+    norms = opt.step().cpu().numpy()
+    pl, gl, nl = ooptim.clip_sgd_library(groups, 0.01)
+    assert nl[0] > 3.0 and nl[1] < 1.0                       # first group clips, second does not
+    np.testing.assert_allclose(norms, nl, rtol=2e-6)
+    for ps, ref_p, ref_g in zip((list(m.parameters()), list(crit.parameters())), pl, gl):
+        for p, rp, rg in zip(ps, ref_p, ref_g):
+            np.testing.assert_allclose(p.grad.cpu().numpy(), rg, rtol=3e-6, atol=1e-9)
+            np.testing.assert_allclose(p.detach().cpu().numpy(), rp, rtol=3e-7, atol=1e-9)
+    assert all(p._version > v for p, v in zip(m.parameters(), versions))     # weight shadows get re-packed
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    # a training step through the fused tail lowers the loss like the stock tail does
+    x = torch.tensor(I.logmel(12, 20, seed=7)).cuda()
+    l0 = crit(m(x).reshape(4, 3, -1))
+    l0.backward()
+    opt.step()
+    with torch.no_grad():
+        l1 = crit(m(x).reshape(4, 3, -1))
+    assert l1.item() < l0.item()
