@@ -101,7 +101,7 @@ struct Work {
   float* xring[8];                  // persistent BPTT: dX ring of layer l >= 1, [3][nt][H/32][64 x 32] fp32
   unsigned *dcnt, *xcnt;            // persistent BPTT progress counters [L][nt], [L][H/32][nt]
   size_t bcnt_bytes;
-  float* wg_tmp;                    // weight gradients: the two split-K partial products [2][4H x H] fp32
+  float* wg_tmp;                    // weight gradients: split-K partial products [2L products][3 slots][4H x H] fp32
   float* colsum_part;               // [chunks, 4H]
   float* gin_ring[8];               // persistent kernel: [kWlGinRing][nt][H/32][64 x 128] fp32 per layer
   unsigned *hcnt, *gcnt;            // persistent kernel: [L][nt] and [L][H/32][nt] progress counters
@@ -147,7 +147,7 @@ static Work layout_work(char* base, const Dims& d, int training) {
       w.dcl[l] = (float*)take(B * H * 4);
       w.xring[l] = l > 0 ? (float*)take((size_t)3 * nt * NS * 2048 * 4) : nullptr;
     }
-    w.wg_tmp = (float*)take((size_t)2 * 4 * H * H * 4);
+    w.wg_tmp = (float*)take((size_t)2 * d.L * 3 * 4 * H * H * 4);   // [2L products][3 partial slots][4H x H]
     w.bcnt_bytes = al256((size_t)d.L * nt * 4) + al256((size_t)d.L * NS * nt * 4);
     w.dcnt = (unsigned*)take(w.bcnt_bytes);
     w.xcnt = w.dcnt + al256((size_t)d.L * nt * 4) / 4;
@@ -548,6 +548,55 @@ struct Profiler {
   int phase[256];
   int created = 0;
 };
+// ------------------------------------------------------------------------------------------ weight-gradient overlap
+// The persistent BPTT kernel occupies 120 of the 148 SMs and walks the frames from T-1 down, so the weight-gradient
+// products over the LATE frames [t0, T) can run on the idle SMs while BPTT is still working on the early frames:
+// a second stream waits (in a one-block kernel) until every 64-row tile of layer l has published dG for the frames
+// >= t0 (the kernel's own release counters, wbptt.cuh), then runs those slices of dW = dG^T X; the main stream runs
+// the early frames after BPTT with the reduction split in two, and a streaming kernel adds the three partials.
+__global__ void wait_frames_kernel(const unsigned* __restrict__ cnt, int nt, unsigned target) {
+  const int j = threadIdx.x;
+  if (j >= nt) return;
+  long long t0 = 0;
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + j) : "memory");
+    if (v >= target) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 4000000000LL) {
+      printf("svb: weight-gradient gate timeout tile %d have %u want %u\n", j, v, target);
+      __trap();
+    }
+    __nanosleep(2000);
+  }
+}
+__global__ void sum3_kernel(const float4* __restrict__ part, float4* __restrict__ out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = part[i], b = part[n4 + i], c = part[2 * n4 + i];
+    out[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+  }
+}
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t dbg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // SVB_WGRAD_DEBUG: fork, gate open, side done, BPTT done, end
+};
+static SideStream* side_stream() {
+  static SideStream tab[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& ss = tab[dev];
+  if (!ss.s) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) { ss.s = nullptr; return nullptr; }
+    if (getenv("SVB_WGRAD_DEBUG"))
+      for (int i = 0; i < 5; ++i) cudaEventCreate(&ss.dbg[i]);
+  }
+  return &ss;
+}
+#define SIDE_DBG(i, stream) do { if (side && side->dbg[i]) cudaEventRecord(side->dbg[i], stream); } while (0)
+static int g_wgrad_overlap = getenv("SVB_WGRAD_OVERLAP") ? atoi(getenv("SVB_WGRAD_OVERLAP")) : 1;   // late-frame weight-gradient slices run beside the persistent BPTT kernel
 static Profiler g_prof;
 static int g_persistent = 1;   // persistent wavefront forward kernel (wlstm.cuh) when the shape allows
 static int g_persistent_bwd = 1;   // persistent wavefront BPTT kernel (wbptt.cuh) when the shape allows
@@ -588,6 +637,17 @@ using namespace svb;
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
 extern "C" int svb_set_persistent_bwd(int on) { g_persistent_bwd = on != 0; return SVB_OK; }
+extern "C" int svb_set_wgrad_overlap(int on) { g_wgrad_overlap = on != 0; return SVB_OK; }
+// Debug (SVB_WGRAD_DEBUG=1): ms since the fork of the last backward: gate of the top layer open, side stream done,
+// BPTT kernel done, backward done.  Synchronises.
+extern "C" int svb_wgrad_overlap_timing(float* out4) {
+  SideStream* side = side_stream();
+  if (!side || !side->dbg[0] || !out4) return SVB_ERR_ARG;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventElapsedTime(&out4[i], side->dbg[0], side->dbg[i + 1]) != cudaSuccess) return SVB_ERR_CUDA;
+  return SVB_OK;
+}
 extern "C" int svb_set_fwd_pair(int on) { g_fwd_pair = on != 0; return SVB_OK; }
 extern "C" int svb_set_bwd_splitk(int on) { g_bwd_splitk = on != 0; return SVB_OK; }
 extern "C" int svb_set_trace_mode(int mode) { g_trace_mode = mode; return SVB_OK; }
@@ -779,7 +839,26 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   colsum_f32_kernel<<<(P + 127) / 128, 128, 0, s>>>(w.dy, grads[4 * L + 1], B, P);
   sgemm_small(w.dy, proj_w, w.dh_last, B, H, P, 0, 0, s);               // dh_last[B,H] = dy W_proj
   SVB_CUDA("projection backward");
-  bool use_wbptt = false;
+  bool use_wbptt = false, overlap = false;
+  SideStream* side = nullptr;
+  int t0 = T;
+  auto wg_slot = [&](int product, int slot) { return w.wg_tmp + ((size_t)product * 3 + slot) * 4 * H * H; };
+  // one slice of dW[4H, N] = dG^T X over `rows` rows of (T*B), both operands MN-major; kz > 1 splits it over gridDim.z
+  auto wgrad_part = [&](const __nv_bfloat16* dg, const __nv_bfloat16* x, int N, int rows, int kz, float* out,
+                        cudaStream_t st) -> int {
+    GemmOperands gg;
+    memset(&gg, 0, sizeof(gg));
+    gg.nterms = 1; gg.M = 4 * H; gg.N = N; gg.K = rows;
+    SVB_TRY(make_operand_map(&gg.ta[0], dg, 4 * H, rows, 4 * H, 1, 0));
+    SVB_TRY(make_operand_map(&gg.tb[0], x, N, rows, N, 1, 0));
+    if (kz > 1) { gg.kz = kz; gg.K = ((rows + kz - 1) / kz + 63) / 64 * 64; }   // TMA zero-fills rows past the end
+    EpiStoreF32<256>::Params ep;
+    SVB_TRY(make_store_params<256>(&ep, out, nullptr, 4 * H, N, (int64_t)N, H));
+    ep.z_stride = (int64_t)4 * H * N;
+    cudaError_t ee = launch_tc_gemm<256, 6, true, true, EpiStoreF32<256>, 8, 1, true>(gg, ep, st);
+    if (ee != cudaSuccess) { set_error("weight gradient slice", ee); return SVB_ERR_CUDA; }
+    return SVB_OK;
+  };
   if (g_persistent_bwd && H == 768 && L <= 3) {
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -804,7 +883,27 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     bp.trace = reinterpret_cast<long long*>(g_trace_bwd);
     bp.B = B; bp.T = T; bp.L = L; bp.H = H; bp.nt = nt;
     cudaMemsetAsync(w.dcnt, 0, w.bcnt_bytes, s);
+    overlap = g_wgrad_overlap && (H % 256 == 0) && T >= 16 && nt <= 1024 && TB >= 4096 && (side = side_stream()) != nullptr;
+    if (overlap) {      // the side stream starts after everything queued so far (counters zeroed, previous call done)
+      cudaEventRecord(side->fork, s);
+      cudaStreamWaitEvent(side->s, side->fork, 0);
+      SIDE_DBG(0, s);
+    }
     SVB_TRY(launch_wbptt<768>(bp, s));
+    if (overlap) {
+      SIDE_DBG(3, s);
+      t0 = T - (3 * T) / 10;                            // late frames [t0, T): ~30 % of the reduction
+      for (int l = L - 1; l >= 0; --l) {
+        wait_frames_kernel<<<1, (nt + 31) / 32 * 32, 0, side->s>>>(w.dcnt + l * nt, nt, (unsigned)((H / 32) * (T - t0)));
+        if (l == L - 1) SIDE_DBG(1, side->s);
+        const size_t r0 = (size_t)t0 * B;
+        SVB_TRY(wgrad_part(w.gates[l] + r0 * 4 * H, w.h_lo[l] + r0 * H, H, TB - (int)r0, 1, wg_slot(2 * l, 2), side->s));
+        if (l > 0) SVB_TRY(wgrad_part(w.gates[l] + r0 * 4 * H, w.h_lo[l - 1] + BH + r0 * H, H, TB - (int)r0, 1, wg_slot(2 * l + 1, 2), side->s));
+      }
+      cudaEventRecord(side->join, side->s);
+      SIDE_DBG(2, side->s);
+      SVB_CUDA("late-frame weight gradients");
+    }
   }
   for (int l = L - 1; l >= 0; --l) {
     const LayerW& lw = pw.l[l];
@@ -860,7 +959,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         gg.kz = 0; gg.K = TB;
         return SVB_OK;
       };
-      if (split2) {
+      if (overlap) {                 // early frames [0, t0) in two slices; the late slice is on the side stream
+        SVB_TRY(wgrad_part(w.gates[l], w.h_lo[l], H, t0 * B, 2, wg_slot(2 * l, 0), s));
+        e = cudaSuccess;
+      } else if (split2) {
         SVB_TRY(wgrad_split2(g, grads[4 * l + 1], H));
         e = cudaSuccess;
       } else if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
@@ -875,7 +977,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
       SVB_TRY(make_operand_map(&g.tb[0], xin, lw.Ip, TB, lw.Ip, 1, 0));
-      if (split2 && lw.I % 256 == 0) {
+      if (overlap && l > 0) {
+        SVB_TRY(wgrad_part(w.gates[l], xin, H, t0 * B, 2, wg_slot(2 * l + 1, 0), s));
+        e = cudaSuccess;
+      } else if (split2 && lw.I % 256 == 0) {
         SVB_TRY(wgrad_split2(g, grads[4 * l], lw.I));
         e = cudaSuccess;
       } else if (lw.I % 128 == 0) {
@@ -888,7 +993,8 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         int kz = 1;
         if (TB >= 4096 && (size_t)4 * H * lw.I * 6 <= (size_t)2 * 4 * H * H) kz = 6;
         EpiStoreF32<128>::Params ep2;
-        SVB_TRY(make_store_params<128>(&ep2, kz > 1 ? w.wg_tmp : grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
+        float* narrow_tmp = overlap ? wg_slot(1, 0) : w.wg_tmp;      // (product 1 = this one: its slots are free)
+        SVB_TRY(make_store_params<128>(&ep2, kz > 1 ? narrow_tmp : grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
         if (kz > 1) {
           g.kz = kz; g.K = ((TB + kz - 1) / kz + 63) / 64 * 64;     // the last slices run past T*B: TMA zero-fill
           ep2.z_stride = (int64_t)4 * H * lw.I;
@@ -896,7 +1002,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
         if (kz > 1 && e == cudaSuccess) {
           const size_t n = (size_t)4 * H * lw.I;
-          sumz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.wg_tmp, grads[4 * l], n, kz);
+          sumz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(narrow_tmp, grads[4 * l], n, kz);
           g.kz = 0; g.K = TB;
         }
       }
@@ -931,6 +1037,17 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       }
       if (e != cudaSuccess) { set_error("dX", e); return SVB_ERR_CUDA; }
     }
+  }
+  if (overlap) {      // join: early slices (this stream) + late slices (side stream) -> gradients
+    prof_mark(PH_WGRAD, s);
+    cudaStreamWaitEvent(s, side->join, 0);
+    const size_t n4 = (size_t)4 * H * H / 4;
+    for (int l = 0; l < L; ++l) {
+      sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l, 0)), reinterpret_cast<float4*>(grads[4 * l + 1]), n4);
+      if (l > 0) sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l + 1, 0)), reinterpret_cast<float4*>(grads[4 * l]), n4);
+    }
+    SVB_CUDA("weight gradient sums");
+    SIDE_DBG(4, s);
   }
   prof_mark(-1, s);
   return SVB_OK;

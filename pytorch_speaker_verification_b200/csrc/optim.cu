@@ -34,15 +34,15 @@ struct OptTable {
   int write_grads;
 };
 
-__device__ __forceinline__ float warp_sum_o(float v) {
+__device__ __forceinline__ double warp_sum_o(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
 // partials[g * gridDim.x + block]
-__global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const OptTable t, float* __restrict__ partials) {
-  __shared__ float red[kOptMaxGroups][kOptThreads / 32];
+__global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const OptTable t, double* __restrict__ partials) {
+  __shared__ double red[kOptMaxGroups][kOptThreads / 32];
   float acc[kOptMaxGroups];
 #pragma unroll
   for (int g = 0; g < kOptMaxGroups; ++g) acc[g] = 0.f;
@@ -66,32 +66,32 @@ __global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const OptTable t, fl
   }
 #pragma unroll
   for (int g = 0; g < kOptMaxGroups; ++g) {
-    const float v = warp_sum_o(acc[g]);
+    const double v = warp_sum_o((double)acc[g]);   // per-thread fp32 sums of ~80 squares, everything above in fp64
     if ((threadIdx.x & 31) == 0) red[g][threadIdx.x >> 5] = v;
   }
   __syncthreads();
   if (threadIdx.x < kOptMaxGroups) {
-    float v = 0.f;
+    double v = 0.0;
     for (int w = 0; w < kOptThreads / 32; ++w) v += red[threadIdx.x][w];
     if ((int)threadIdx.x < t.ng) partials[threadIdx.x * gridDim.x + blockIdx.x] = v;
   }
 }
 
-__global__ void __launch_bounds__(kOptThreads) clip_sgd_kernel(const OptTable t, const float* __restrict__ partials,
+__global__ void __launch_bounds__(kOptThreads) clip_sgd_kernel(const OptTable t, const double* __restrict__ partials,
                                                                int nparts, float* __restrict__ norms_out) {
-  __shared__ float red[kOptThreads / 32];
+  __shared__ double red[kOptThreads / 32];
   __shared__ float coef_s[kOptMaxGroups];
   for (int g = 0; g < t.ng; ++g) {   // same fixed-order reduction in every block
-    float v = 0.f;
+    double v = 0.0;
     for (int i = threadIdx.x; i < nparts; i += kOptThreads) v += partials[g * nparts + i];
     v = warp_sum_o(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float tot = 0.f;
+      double tot = 0.0;
       for (int w = 0; w < kOptThreads / 32; ++w) tot += red[w];
-      const float norm = sqrtf(tot);
+      const float norm = (float)sqrt(tot);
       float c = t.max_norm[g] / (norm + 1e-6f);      // clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6)
       if (!(t.max_norm[g] > 0.f)) c = 1.0f;          // max_norm <= 0: clipping disabled for this group
       coef_s[g] = c < 1.0f ? c : 1.0f;               // torch.clamp(clip_coef, max=1.0)
@@ -134,7 +134,7 @@ using namespace svb;
 
 extern "C" int svb_clip_sgd_workspace_bytes(size_t* bytes) {
   if (!bytes) return SVB_ERR_ARG;
-  *bytes = (size_t)kOptMaxGroups * kOptMaxBlocks * sizeof(float);
+  *bytes = (size_t)kOptMaxGroups * kOptMaxBlocks * sizeof(double);
   return SVB_OK;
 }
 
@@ -142,7 +142,7 @@ extern "C" int svb_clip_sgd(void* const* params, void* const* grads, const int64
                             int n_tensors, const float* max_norm, int n_groups, float lr, int write_clipped_grads,
                             float* norms_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!params || !grads || !numel || !group || !max_norm || !workspace || n_tensors < 1 || n_tensors > kOptMaxTensors ||
-      n_groups < 1 || n_groups > kOptMaxGroups || workspace_bytes < (size_t)kOptMaxGroups * kOptMaxBlocks * sizeof(float)) {
+      n_groups < 1 || n_groups > kOptMaxGroups || workspace_bytes < (size_t)kOptMaxGroups * kOptMaxBlocks * sizeof(double)) {
     set_error("svb_clip_sgd: bad argument (<= 32 tensors, <= 4 clip groups)", cudaSuccess);
     return SVB_ERR_ARG;
   }
@@ -163,7 +163,7 @@ extern "C" int svb_clip_sgd(void* const* params, void* const* grads, const int64
   long long want = (total / 4 + kOptThreads - 1) / kOptThreads;
   int grid = (int)(want < 1 ? 1 : want > kOptMaxBlocks ? kOptMaxBlocks : want);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  float* partials = static_cast<float*>(workspace);
+  double* partials = static_cast<double*>(workspace);
   sumsq_kernel<<<grid, kOptThreads, 0, s>>>(t, partials);
   clip_sgd_kernel<<<grid, kOptThreads, 0, s>>>(t, partials, grid, norms_out);
   cudaError_t e = cudaGetLastError();

@@ -51,6 +51,12 @@ def set_persistent_bwd(on):
     check(_lib.lib().svb_set_persistent_bwd(int(bool(on))), "svb_set_persistent_bwd")
 
 
+def set_wgrad_overlap(on):
+    """True (default): the weight-gradient products over the late frames run on a second stream beside the persistent
+    BPTT kernel (which leaves 28 SMs idle); False: all of them after it."""
+    check(_lib.lib().svb_set_wgrad_overlap(int(bool(on))), "svb_set_wgrad_overlap")
+
+
 def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 

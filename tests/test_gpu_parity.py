@@ -321,6 +321,31 @@ def test_persistent_bptt_matches_per_frame_bptt(svb, net):
         ops.set_persistent_bwd(True)
 
 
+def test_weight_gradient_overlap_matches_serial(svb, net):
+    """Late-frame weight-gradient slices running beside the BPTT kernel (gated by its release counters) against the
+    same products computed after it: identical up to the fp32 order of three partial sums; repeated, because a slice
+    that started before its dG frames were complete would read gate activations instead of gradients."""
+    from pytorch_speaker_verification_b200 import ops
+    try:
+        for (B, T) in ((640, 40), (128, 64), (70, 160)):
+            x = torch.tensor(I.logmel(B, T, seed=B + T)).cuda()
+            ref = None
+            for mode, reps in ((False, 1), (True, 6)):
+                ops.set_wgrad_overlap(mode)
+                for _ in range(reps):
+                    net.zero_grad()
+                    e = net(x)
+                    e.square().sum().mul(0.5).add(e.sum()).backward()
+                    torch.cuda.synchronize()
+                    got = {k: p.grad.clone() for k, p in net.named_parameters()}
+                    if ref is None:
+                        ref = got
+                    for k in got:
+                        assert rel_l2(got[k].cpu().numpy(), ref[k].cpu().numpy()) < 1e-5, (B, T, mode, k)
+    finally:
+        ops.set_wgrad_overlap(True)
+
+
 def test_persistent_kernel_no_stale_reads(svb, net):
     """Flag protocol of the persistent kernel under a NaN-poisoned workspace: a tile read before its producer's
     stores are visible shows up as NaN (this is how the missing release on the h-tile counter was found).  Small
@@ -440,11 +465,13 @@ def test_fused_clip_sgd_matches_clip_grad_norm_and_sgd(svb, net):
     norms = opt.step().cpu().numpy()
     pl, gl, nl = ooptim.clip_sgd_library(groups, 0.01)
     assert nl[0] > 3.0 and nl[1] < 1.0                       # first group clips, second does not
-    np.testing.assert_allclose(norms, nl, rtol=2e-6)
+    exact = [np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for _, g in pg)) for pg, _ in groups]
+    np.testing.assert_allclose(norms, exact, rtol=1e-6)      # fp64 above the per-thread sums
+    np.testing.assert_allclose(norms, nl, rtol=2e-4)         # the library's own fp32 norm-of-norms (3.7e-5 off here)
     for ps, ref_p, ref_g in zip((list(m.parameters()), list(crit.parameters())), pl, gl):
         for p, rp, rg in zip(ps, ref_p, ref_g):
-            np.testing.assert_allclose(p.grad.cpu().numpy(), rg, rtol=3e-6, atol=1e-9)
-            np.testing.assert_allclose(p.detach().cpu().numpy(), rp, rtol=3e-7, atol=1e-9)
+            np.testing.assert_allclose(p.grad.cpu().numpy(), rg, rtol=2e-4, atol=1e-9)     # inherits the norm difference
+            np.testing.assert_allclose(p.detach().cpu().numpy(), rp, rtol=3e-7, atol=2e-9)
     assert all(p._version > v for p, v in zip(m.parameters(), versions))     # weight shadows get re-packed
     opt.zero_grad()
     assert all(p.grad is None for p in m.parameters())
