@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace cg = cooperative_groups;
@@ -63,6 +64,7 @@ struct Ge2eArgs {
   float* dC;             // [Nc, D]  P = A_off^T E^ (numerator of the centroid gradient)
   float* R;              // [N*M, D] A_off C^
   long long* trace;      // debug (SVB_GE2E_TRACE=1): [N, 16] clock64 stamps of the per-speaker kernel, else null
+  unsigned* bar;         // per-speaker kernel, cluster form: the word of its own grid barrier
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -490,12 +492,36 @@ __host__ __device__ inline SpkLayout spk_layout(int N, int DH, int MP) {
   return l;
 }
 
+// Grid barrier of the cluster form (a plain cluster launch: Nsight Compute refuses cooperative + cluster launches, and
+// all CL * N <= #SMs CTAs are co-resident at one CTA per SM).  One word, self-resetting: every CTA adds 1, CTA 0 adds
+// 2^31 - (nblocks - 1), so a complete round adds exactly 2^31: the top bit flips and the low bits return to where they
+// were.  One release atomic + acquire polls per CTA (separate fences cost ~1000 cycles each with stores in flight);
+// the other threads are ordered through the two CTA barriers.  The word is library-owned and zeroed once.
+__device__ __forceinline__ void spk_grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned inc = blockIdx.x == 0 ? 0x80000000u - (nblocks - 1) : 1u;
+    unsigned old, v;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(bar), "r"(inc) : "memory");
+    long long t0 = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((old ^ v) & 0x80000000u) break;
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) { printf("svb: ge2e grid barrier timeout block %d\n", blockIdx.x); __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
 template <int MP, int CL>
 __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) {
   constexpr int MS = (MP + 3) & ~3;       // row stride of the [k][m] arrays (float4 loads)
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  cg::grid_group grid = cg::this_grid();
+  auto grid_sync = [&]() {
+    if constexpr (CL > 1) spk_grid_barrier(a.bar, gridDim.x); else cg::this_grid().sync();
+  };
   const int N = a.N, M = a.M, D = a.D, NM = N * M;
   const int h = CL > 1 ? (int)(blockIdx.x % CL) : 0;           // rank in the cluster = which slice of D
   const int j = blockIdx.x / CL;
@@ -588,7 +614,7 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
     }
   }
   if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 1] = clock64();
-  grid.sync();
+  grid_sync();
   if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 2] = clock64();
 
   // ------------------------------------------------------------------ phase 2
@@ -715,7 +741,7 @@ __global__ void __launch_bounds__(kST, 1) ge2e_speaker_kernel(const Ge2eArgs a) 
     }
   }
   if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 6] = clock64();
-  grid.sync();
+  grid_sync();
   if (a.trace && tid == 0) a.trace[blockIdx.x * 16 + 7] = clock64();
 
   // ------------------------------------------------------------------ phase 3
@@ -910,7 +936,7 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   if (b2blocks > want) want = b2blocks;
   if (fused == 1 && spk_candidate(N, M, D, Nc) && !Cext && w && !dcos && !cos_out && N <= num_sms) {
     // small batch (the reference's training batch): one CTA or one 2-CTA cluster per speaker, three phases
-    static int cluster_ok = 1;                       // cleared if the cooperative + cluster launch is refused
+    static int cluster_ok = 1;                       // cleared if the cluster launch is refused
     const int MP = (M + 1) & ~1;
     for (int CL = (cluster_ok && D % 8 == 0 && 2 * N <= num_sms) ? 2 : 1; CL >= 1; --CL) {
       const size_t sm = spk_layout(N, D / CL, MP).floats * sizeof(float);
@@ -922,13 +948,28 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
         if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute (speaker kernel)", e); return SVB_ERR_CUDA; }
         spk_smem_set[CL - 1][MP / 2 - 1] = (int)sm;
       }
+      if (CL > 1) {
+        static unsigned* bar_tab[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) continue;
+        if (!bar_tab[dev]) {
+          if (cudaMalloc(&bar_tab[dev], 256) != cudaSuccess || cudaMemset(bar_tab[dev], 0, 256) != cudaSuccess) {
+            cudaGetLastError(); bar_tab[dev] = nullptr; cluster_ok = 0; continue;
+          }
+        }
+        a.bar = bar_tab[dev];
+      }
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(kST); cfg.dynamicSmemBytes = sm; cfg.stream = s;
       cudaLaunchAttribute at[2];
-      at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-      at[1].id = cudaLaunchAttributeClusterDimension;
-      at[1].val.clusterDim.x = CL; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = CL > 1 ? 2 : 1;
+      if (CL > 1) {       // plain cluster launch + the kernel's own grid barrier
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      } else {
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+      }
+      cfg.attrs = at; cfg.numAttrs = 1;
       void* params[] = {&a};
       cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
       if (e == cudaSuccess) return SVB_OK;
