@@ -8,3 +8,4 @@ from .utils import calc_loss, get_centroids, get_cossim              # noqa: F40
 from .eer import compute_eer, eer_sweep                              # noqa: F401
 from .dvector import align_embeddings, extract_dvectors, get_windows  # noqa: F401
 from .optim import FusedClipSGD                                       # noqa: F401
+from .staging import prefetch                                         # noqa: F401

@@ -66,39 +66,114 @@ def _cached_partition_offsets(W):
     return po
 
 
+class _PinnedPool:
+    """Reusable page-locked staging buffers (cudaHostAlloc costs milliseconds; extraction is called per file list)."""
+
+    def __init__(self):
+        self.free = []
+
+    def take(self, nbytes):
+        best = None
+        for i, t in enumerate(self.free):
+            if t.numel() >= nbytes and (best is None or t.numel() < self.free[best].numel()):
+                best = i
+        if best is not None:
+            return self.free.pop(best)
+        return torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
+
+    def give(self, t):
+        self.free.append(t)
+
+
+_pool = _PinnedPool()
+
+
+def _chunk_plan(Ts):
+    """Index math of one chunk of utterances with frame counts Ts: window start frames (in the concatenated chunk),
+    partition offsets, partitions per utterance."""
+    nw = np.where(Ts > WIN, -(-(Ts - WIN) // HOP), 0)                     # windows per utterance (strict j+24 < T)
+    base = np.concatenate([[0], np.cumsum(Ts)[:-1]])                      # first frame of each utterance
+    W = int(nw.sum())
+    wfirst = np.concatenate([[0], np.cumsum(nw)[:-1]])                    # first window index of each utterance
+    within = np.arange(W, dtype=np.int64) - np.repeat(wfirst, nw)
+    starts = (np.repeat(base, nw) + HOP * within).astype(np.int32)
+    seg, counts = [np.zeros(1, dtype=np.int64)], []
+    for n, w0 in zip(nw.tolist(), wfirst.tolist()):
+        if n:
+            po = _cached_partition_offsets(n)
+            seg.append(po[1:].astype(np.int64) + w0)
+            counts.append(len(po) - 1)
+        else:
+            counts.append(0)
+    return W, starts, np.concatenate(seg).astype(np.int32), counts
+
+
 @torch.no_grad()
-def extract_dvectors(embedder_net, specs, max_windows=65536):
+def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 16):
     """Batched extraction for many utterances: specs = list of (nmels, T_u) log-mel arrays.
-    Returns a list of (P_u, D) float64 arrays (empty (0, D) for utterances with no window).  One window-gather
-    launch and one segment-mean launch for the whole batch; the LSTM runs on chunks of <= max_windows windows."""
+    Returns a list of (P_u, D) float64 arrays (empty (0, D) for utterances with no window).
+
+    The utterances are processed in chunks of about ``chunk_frames`` frames: per chunk one pinned staging copy, one
+    asynchronous H2D copy, one window-gather launch, the LSTM on <= max_windows windows at a time, one segment-mean
+    launch and an asynchronous D2H copy into pinned memory.  Nothing synchronises until the last chunk is queued, so
+    the host-side staging and index math of chunk i+1 overlap the GPU work of chunk i."""
     dev = ops._dev()
+    D = embedder_net.projection.out_features
+    n = len(specs)
+    if n == 0:
+        return []
+    nmels = int(specs[0].shape[0])
+    Ts_all = np.asarray([int(s.shape[1]) for s in specs], dtype=np.int64)
+    # chunk boundaries by cumulative frames
+    bounds, acc = [0], 0
+    for i, T in enumerate(Ts_all.tolist()):
+        acc += T
+        if acc >= chunk_frames:
+            bounds.append(i + 1)
+            acc = 0
+    if bounds[-1] != n:
+        bounds.append(n)
+    pending, held = [], []
     with torch.cuda.device(dev):
-        Ts = np.asarray([int(s.shape[1]) for s in specs], dtype=np.int64)
-        cat = torch.from_numpy(np.concatenate([np.asarray(s, dtype=np.float32) for s in specs], axis=1))
-        cat = cat.pin_memory().to(dev, non_blocking=True)
-        nw = np.where(Ts > WIN, -(-(Ts - WIN) // HOP), 0)                 # windows per utterance (strict j+24 < T)
-        base = np.concatenate([[0], np.cumsum(Ts)[:-1]])                  # first frame of each utterance
-        W = int(nw.sum())
-        D = embedder_net.projection.out_features
-        if W == 0:
-            return [np.zeros((0, D)) for _ in specs]
-        wfirst = np.concatenate([[0], np.cumsum(nw)[:-1]])               # first window index of each utterance
-        within = np.arange(W, dtype=np.int64) - np.repeat(wfirst, nw)
-        starts = (np.repeat(base, nw) + HOP * within).astype(np.int32)
-        seg, counts = [np.zeros(1, dtype=np.int64)], []
-        for n, w0 in zip(nw.tolist(), wfirst.tolist()):
-            if n:
-                po = _cached_partition_offsets(n)
-                seg.append(po[1:].astype(np.int64) + w0)
-                counts.append(len(po) - 1)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            Ts = Ts_all[lo:hi]
+            F = int(Ts.sum())
+            W, starts, seg, counts = _chunk_plan(Ts)
+            if W == 0:
+                pending.append((None, 0, counts))
+                continue
+            # one staging buffer: [log-mel (nmels, F) float32 | starts int32 | seg int32]
+            nb_spec, nb_st, nb_seg = nmels * F * 4, starts.size * 4, seg.size * 4
+            stage = _pool.take(nb_spec + nb_st + nb_seg)
+            sv = stage.numpy()
+            np.concatenate([np.asarray(s, dtype=np.float32) for s in specs[lo:hi]], axis=1,
+                           out=sv[:nb_spec].view(np.float32).reshape(nmels, F))
+            sv[nb_spec:nb_spec + nb_st].view(np.int32)[:] = starts
+            sv[nb_spec + nb_st:nb_spec + nb_st + nb_seg].view(np.int32)[:] = seg
+            g = stage[:nb_spec + nb_st + nb_seg].to(dev, non_blocking=True)
+            cat = g[:nb_spec].view(torch.float32).view(nmels, F)
+            st_d = g[nb_spec:nb_spec + nb_st].view(torch.int32)
+            seg_d = g[nb_spec + nb_st:].view(torch.int32)
+            frames = ops.dvector_windows(cat, st_d, WIN)
+            if W <= max_windows:
+                emb = embedder_net(frames)
             else:
-                counts.append(0)
-        seg = np.concatenate(seg).astype(np.int32)
-        frames = ops.dvector_windows(cat, torch.from_numpy(starts).to(dev), WIN)
-        emb = torch.cat([embedder_net(frames[i:i + max_windows]) for i in range(0, W, max_windows)], dim=0)
-        out = ops.segment_mean(emb, torch.from_numpy(seg).to(dev)).cpu().numpy()
-    res, o = [], 0
-    for c in counts:
-        res.append(out[o:o + c])
-        o += c
+                emb = torch.cat([embedder_net(frames[i:i + max_windows]) for i in range(0, W, max_windows)], dim=0)
+            out = ops.segment_mean(emb, seg_d)                             # (P, D) float64
+            P = int(out.shape[0])
+            host = _pool.take(P * D * 8)
+            hv = host[:P * D * 8].view(torch.float64).view(P, D)
+            hv.copy_(out, non_blocking=True)
+            pending.append((hv, P, counts))
+            held += [stage, host]
+        torch.cuda.current_stream().synchronize()
+    res = []
+    for hv, P, counts in pending:
+        o = 0
+        arr = hv.numpy() if hv is not None else None
+        for c in counts:
+            res.append(np.array(arr[o:o + c]) if c else np.zeros((0, D)))
+            o += c
+    for t in held:
+        _pool.give(t)
     return res

@@ -245,6 +245,18 @@ def test_extract_dvectors_batched_equals_per_file(svb, net):
         np.testing.assert_allclose(o, svb.align_embeddings(emb.cpu().numpy()), atol=2e-6)
         ref = odv.align_embeddings(emb.cpu().numpy())
         np.testing.assert_array_equal(svb.align_embeddings(emb.cpu().numpy()), ref)
+    # chunked pipeline: many small chunks (incl. chunks whose utterances have no window) == one chunk, twice (the
+    # pinned staging buffers are reused between calls)
+    lens = [int(t) for t in rng.randint(10, 400, size=40)] + [24, 25, 12]
+    many = [np.log10(I.power_spec(T, seed=T) + 1e-6).astype(np.float32) for T in lens]
+    one = svb.extract_dvectors(net, many, chunk_frames=1 << 30)
+    for _ in range(2):
+        small = svb.extract_dvectors(net, many, chunk_frames=300)
+        assert len(small) == len(one) == len(many)
+        for a, b in zip(small, one):
+            assert a.shape == b.shape
+            np.testing.assert_allclose(a, b, atol=2e-6)
+    assert svb.extract_dvectors(net, []) == []
 
 
 # ----------------------------------------------------------------------------------------------- embedder
@@ -483,3 +495,16 @@ def test_fused_clip_sgd_matches_clip_grad_norm_and_sgd(svb, net):
     with torch.no_grad():
         l1 = crit(m(x).reshape(4, 3, -1))
     assert l1.item() < l0.item()
+
+
+def test_prefetch_yields_every_batch_in_order(svb):
+    """staging.prefetch: (N, M, T, F) host batches arrive on the device reshaped to (N*M, T, F), in order, through
+    reused page-locked buffers (more batches than buffers)."""
+    r = np.random.RandomState(0)
+    batches = [torch.tensor(r.randn(3, 2, 5 + i, 4).astype(np.float32)) for i in range(7)]
+    got = list(svb.prefetch(batches, "cuda", depth=2))
+    assert len(got) == len(batches)
+    for b, g in zip(batches, got):
+        assert g.is_cuda and g.shape == (6, b.shape[2], 4)
+        assert torch.equal(g.cpu(), b.reshape(6, b.shape[2], 4))
+    assert list(svb.prefetch([], "cuda")) == []
