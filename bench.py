@@ -177,6 +177,27 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
     if rank != 0:
         return out
 
+    # ---- the LSTM input projection as a standalone batched GEMM (north_star: tensor-pipe utilisation of the input
+    # GEMM; in the default path this product is fused into the persistent forward kernel): all 160 frames x 640
+    # utterances of layer 1/2, [102400 x 768] . [768 x 3072], bf16 operands, fp32 out, CTA-pair tcgen05 tiles
+    Mg, Ng, Kg = 640 * 160, 3072, 768
+    Ag = torch.randn(Mg, Kg, device=dev).to(torch.bfloat16)
+    Bg = (torch.randn(Ng, Kg, device=dev) * 0.05).to(torch.bfloat16)
+    Cg = torch.empty(Mg, Ng, device=dev)
+    PA = (ctypes.c_void_p * 1)(Ag.data_ptr())
+    PB = (ctypes.c_void_p * 1)(Bg.data_ptr())
+
+    def input_gemm():
+        L.svb_gemm_bf16_2cta(PA, PB, 1, ptr(Cg), None, Mg, Ng, Kg, ctypes.c_int64(Kg), ctypes.c_int64(Kg),
+                             ctypes.c_int64(Ng), 0, stream_ptr())
+
+    ms = dev_time(input_gemm, 10, 3)
+    tf = 2.0 * Mg * Ng * Kg / (ms * 1e-3) / 1e12
+    out["lstm_input_gemm_standalone"] = {"M": Mg, "N": Ng, "K": Kg, "ms": ms, "tflops": tf,
+                                         "frac_of_sustained_bf16_peak": tf / peaks()[0].get("bf16_tflops_sustained", 1400.0),
+                                         "kernel": "tc_gemm_kernel<256,6,K-major,pair> (cta_group::2, 256x256 pair tiles)"}
+    del Ag, Bg, Cg
+
     # ---- EER sweep at N=1024, M=6 (3 enrollment + 3 verification)
     enr, ver = I.eer_embeddings(1024, 6, 0.06, 0.5, 4242)
     enr, ver = torch.tensor(enr).to(dev), torch.tensor(ver).to(dev)

@@ -508,3 +508,47 @@ def test_prefetch_yields_every_batch_in_order(svb):
         assert g.is_cuda and g.shape == (6, b.shape[2], 4)
         assert torch.equal(g.cpu(), b.reshape(6, b.shape[2], 4))
     assert list(svb.prefetch([], "cuda")) == []
+
+
+# ----------------------------------------------------------------------------------------------- BASELINE full sizes
+def test_full_size_c2_embedder_properties(svb, net):
+    """BASELINE configs[1] size (640 utterances x 160 frames): a sample of rows against the fp32 oracle, unit norms,
+    batch independence at full size, and linearity of the parameter gradients in the batch (loss separable per row:
+    grads(640 rows) = grads(first 320) + grads(last 320))."""
+    xn = I.logmel(640, 160, seed=1234)
+    x = torch.tensor(xn).cuda()
+    with torch.no_grad():
+        full = net(x)
+        assert torch.equal(net(x[100:164]), full[100:164])
+        np.testing.assert_allclose(full.norm(dim=1).cpu().numpy(), 1.0, atol=2e-6)
+        sd = oemb.init_state_dict(seed=0)
+        rows = [0, 77, 319, 320, 500, 639]
+        e_ref = oemb.embedder_explicit(torch.tensor(xn[rows]), sd).numpy()
+    assert emb_err(full[rows].cpu().numpy(), e_ref) < 1e-3
+    grads = []
+    for part in (x, x[:320], x[320:]):
+        net.zero_grad()
+        e = net(part)
+        e.square().sum().mul(0.5).add(e[:, :7].sum()).backward()
+        grads.append({k: p.grad.double().clone() for k, p in net.named_parameters()})
+    for k in grads[0]:
+        assert rel_l2((grads[1][k] + grads[2][k]).cpu().numpy(), grads[0][k].cpu().numpy()) < 2e-3, k
+
+
+def test_full_size_c3_ge2e_and_c5_eer(svb):
+    """BASELINE configs[2] loss (N = 512 x M = 10, the global batch every rank evaluates) against the fp64 closed form,
+    and configs[4] (EER at N = 1024, M = 6): the kernel's tuple equals the oracle sweep over the same similarities."""
+    Enp = I.ge2e_embeddings(512, 10, 256, "clustered")
+    o = oge2e.ge2e_fwd_bwd(Enp.astype(np.float64), 10.0, -5.0)
+    E = torch.tensor(Enp, device="cuda", requires_grad=True)
+    crit = svb.GE2ELoss("cuda")
+    loss = crit(E)
+    loss.backward()
+    assert rel(loss.item(), o["loss"]) < 1e-5
+    assert rel(E.grad.cpu().numpy(), o["dE"]) < 1e-5
+    assert rel(crit.w.grad.item(), o["dw"]) < 1e-5
+    enr, ver = I.eer_embeddings(1024, 6, 0.06, 0.5, 4242)
+    tup, sim = svb.compute_eer(torch.tensor(enr, device="cuda"), torch.tensor(ver, device="cuda"))
+    assert sim.shape == (1024, 3, 1024)
+    assert [float(v) for v in tup] == [float(v) for v in oeer.eer_sweep(sim.cpu().numpy())]
+    assert 0.0 < float(tup[0]) < 0.5
