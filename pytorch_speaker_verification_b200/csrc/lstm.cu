@@ -96,6 +96,7 @@ struct Work {
   float* c[8];                      // [cslots, B, H]
   __nv_bfloat16* gates[8];          // [T+1, B, 4H] (training)
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
+  float* proj_part;                 // [kProjSlices][B,P] split-K partials of the projection
   float *dh_above, *dc, *dh_last, *dy;  // backward: [T,B,H], [B,H], [B,H], [B,P]
   float* dcl[8];                    // persistent BPTT: running dL/dc per layer [B,H]
   float* xring[8];                  // persistent BPTT: dX ring of layer l >= 1, [3][nt][H/32][64 x 32] fp32
@@ -110,6 +111,7 @@ struct Work {
   size_t bytes;
 };
 constexpr int kColsumRows = 256;
+constexpr int kProjSlices = 3;      // the projection GEMM (K = H) is split three ways to fill the machine
 static Work layout_work(char* base, const Dims& d, int training) {
   Work w{};
   size_t off = 0;
@@ -129,6 +131,7 @@ static Work layout_work(char* base, const Dims& d, int training) {
   w.h_last = (float*)take(B * H * 4);
   w.y = (float*)take(B * d.P * 4);
   w.inv_norm = (float*)take(B * 4);
+  w.proj_part = (float*)take((size_t)kProjSlices * B * d.P * 4);
   {
     const size_t nt = (B + 63) / 64, NS = H / 32;
     for (int l = 0; l < d.L; ++l) w.gin_ring[l] = (float*)take((size_t)3 * nt * NS * 8192 * 4);
@@ -385,56 +388,6 @@ static_assert(kWlGinRing == 3, "layout_work sizes the gin ring for 3 frames");
 static_assert(kWbXRing == 3, "layout_work sizes the dX ring for 3 frames");
 
 // ------------------------------------------------------------------------------------------ projection + L2 norm
-// y[b,:] = W h_last[b,:] + bias; emb = y/|y|   (speech_embedder_net.py:31-32; fp32; 8 batch rows per CTA)
-constexpr int kProjRows = 8;
-__global__ void __launch_bounds__(256) proj_norm_kernel(const float* __restrict__ h, const float* __restrict__ W,
-                                                        const float* __restrict__ bias, float* __restrict__ y,
-                                                        float* __restrict__ inv_norm, float* __restrict__ emb, int B,
-                                                        int H, int P) {
-  extern __shared__ float sm[];
-  float* hs = sm;                        // [kProjRows][H]
-  float* ys = sm + kProjRows * H;        // [kProjRows][P]
-  __shared__ float inv[kProjRows];
-  const int b0 = blockIdx.x * kProjRows;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kProjRows * H; i += 256) {
-    const int r = i / H;
-    hs[i] = (b0 + r < B) ? h[(size_t)(b0 + r) * H + (i % H)] : 0.f;
-  }
-  __syncthreads();
-  for (int p = warp; p < P; p += 8) {
-    float acc[kProjRows];
-#pragma unroll
-    for (int r = 0; r < kProjRows; ++r) acc[r] = 0.f;
-    for (int k = lane; k < H; k += 32) {
-      const float wv = W[(size_t)p * H + k];
-#pragma unroll
-      for (int r = 0; r < kProjRows; ++r) acc[r] += wv * hs[r * H + k];
-    }
-#pragma unroll
-    for (int r = 0; r < kProjRows; ++r) {
-      float v = acc[r];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) ys[r * P + p] = v + bias[p];
-    }
-  }
-  __syncthreads();
-  if (warp < kProjRows) {
-    float ss = 0.f;
-    for (int p = lane; p < P; p += 32) ss += ys[warp * P + p] * ys[warp * P + p];
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) inv[warp] = 1.0f / sqrtf(ss);          // no epsilon (speech_embedder_net.py:32)
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kProjRows * P; i += 256) {
-    const int r = i / P, b = b0 + r;
-    if (b < B) {
-      y[(size_t)b * P + (i % P)] = ys[i];
-      emb[(size_t)b * P + (i % P)] = ys[i] * inv[r];
-      if ((i % P) == 0) inv_norm[b] = inv[r];
-    }
-  }
-}
 // dy = (de - (de.e) e) / |y|  with e = y/|y|
 __global__ void norm_bwd_kernel(const float* __restrict__ de, const float* __restrict__ y,
                                 const float* __restrict__ inv_norm, float* __restrict__ dy, int B, int P) {
@@ -449,42 +402,123 @@ __global__ void norm_bwd_kernel(const float* __restrict__ de, const float* __res
     dy[(size_t)b * P + p] = (de[(size_t)b * P + p] - dot * e) * inv;
   }
 }
-// Small fp32 SIMT GEMM: C[M,N] = op(A) op(B); 32x32 tiles.  ta: A stored [K,M]; tb: B stored [N,K].
-__global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                                          float* __restrict__ C, int M, int N, int K, int ta, int tb) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    for (int i = ty; i < 32; i += 8) {
-      // As[i][tx] = A(m0+i, k0+tx) ; Bs[i][tx] = B(k0+i, n0+tx)
-      int m = m0 + i, k = k0 + tx;
-      float av = 0.f;
-      if (ta) { int mm = m0 + tx, kk = k0 + i; if (mm < M && kk < K) av = A[(size_t)kk * M + mm]; As[tx][i] = av; }
-      else { if (m < M && k < K) av = A[(size_t)m * K + k]; As[i][tx] = av; }
-      float bv = 0.f;
-      if (tb) { int nn = n0 + i, kk = k0 + tx; if (nn < N && kk < K) bv = Bm[(size_t)nn * K + kk]; Bs[tx][i] = bv; }
-      else { int kk = k0 + i, nn = n0 + tx; if (kk < K && nn < N) bv = Bm[(size_t)kk * N + nn]; Bs[i][tx] = bv; }
-    }
-    __syncthreads();
+// fp32 SIMT GEMM for the projection head (speech_embedder_net.py:31 and its backward): 64 x 64 tiles, 4 x 4 outputs
+// per thread, K staged 32 at a time with the next chunk's loads in flight; generic strides so that the same kernel
+// serves y = h W^T, dW = dy^T h and dh = dy W without transposed copies; blockIdx.z = slice of the reduction
+// (partials at C + z * zstride, summed by the caller's finishing kernel).
+//   C[z][m, n] = sum_{k in slice z} A(m, k) B(n, k),  A(m, k) = A[m sam + k sak],  B(n, k) = B[n sbn + k sbk]
+constexpr int kSgT = 64, kSgK = 32, kSgLd = kSgT * kSgK / 256;
+__device__ __forceinline__ void sg_fetch(const float* __restrict__ P, int64_t sr, int64_t sk, int R, int k1, int r0,
+                                         int k0, float (&v)[kSgLd]) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float bv = Bs[k][tx];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] += As[ty + 8 * r][k] * bv;
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int m = m0 + ty + 8 * r, n = n0 + tx;
-    if (m < M && n < N) C[(size_t)m * N + n] = acc[r];
+  for (int i = 0; i < kSgLd; ++i) {
+    const int e = threadIdx.x + i * 256;
+    int r, k;
+    if (sk == 1) { k = e % kSgK; r = e / kSgK; } else { r = e % kSgT; k = e / kSgT; }
+    const int gr = r0 + r, gk = k0 + k;
+    v[i] = (gr < R && gk < k1) ? __ldg(P + gr * sr + gk * sk) : 0.f;
   }
 }
-static void sgemm_small(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t s) {
-  dim3 grid((N + 31) / 32, (M + 31) / 32);
-  sgemm_small_kernel<<<grid, 256, 0, s>>>(A, B, C, M, N, K, ta, tb);
+__device__ __forceinline__ void sg_stash(float (*S)[kSgT + 4], int64_t sk, const float (&v)[kSgLd]) {
+#pragma unroll
+  for (int i = 0; i < kSgLd; ++i) {
+    const int e = threadIdx.x + i * 256;
+    int r, k;
+    if (sk == 1) { k = e % kSgK; r = e / kSgK; } else { r = e % kSgT; k = e / kSgT; }
+    S[k][r] = v[i];
+  }
+}
+__global__ void __launch_bounds__(256) sgemm64_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
+                                                      const float* __restrict__ Bm, int64_t sbn, int64_t sbk,
+                                                      float* __restrict__ C, int64_t ldc, int64_t zstride, int M, int N,
+                                                      int K, int kslice) {
+  __shared__ __align__(16) float As[kSgK][kSgT + 4];
+  __shared__ __align__(16) float Bs[kSgK][kSgT + 4];
+  const int m0 = blockIdx.y * kSgT, n0 = blockIdx.x * kSgT;
+  const int kb = blockIdx.z * kslice, ke = kb + kslice < K ? kb + kslice : K;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float va[kSgLd], vb[kSgLd];
+  sg_fetch(A, sam, sak, M, ke, m0, kb, va);
+  sg_fetch(Bm, sbn, sbk, N, ke, n0, kb, vb);
+  for (int k0 = kb; k0 < ke; k0 += kSgK) {
+    __syncthreads();
+    sg_stash(As, sak, va);
+    sg_stash(Bs, sbk, vb);
+    __syncthreads();
+    if (k0 + kSgK < ke) {
+      sg_fetch(A, sam, sak, M, ke, m0, k0 + kSgK, va);
+      sg_fetch(Bm, sbn, sbk, N, ke, n0, k0 + kSgK, vb);
+    }
+#pragma unroll
+    for (int k = 0; k < kSgK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+  }
+  float* Cz = C + (int64_t)blockIdx.z * zstride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + 4 * ty + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + 4 * tx + j;
+      if (gn < N) Cz[(int64_t)gm * ldc + gn] = acc[i][j];
+    }
+  }
+}
+static void sgemm64(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t sbn, int64_t sbk, float* C,
+                    int64_t ldc, int M, int N, int K, int kz, cudaStream_t s) {
+  const int kslice = ((K + kz - 1) / kz + kSgK - 1) / kSgK * kSgK;
+  dim3 grid((N + kSgT - 1) / kSgT, (M + kSgT - 1) / kSgT, (K + kslice - 1) / kslice);
+  sgemm64_kernel<<<grid, 256, 0, s>>>(A, sam, sak, Bm, sbn, sbk, C, ldc, (int64_t)M * ldc, M, N, K, kslice);
+}
+static int sgemm64_slices(int K, int kz) {
+  const int kslice = ((K + kz - 1) / kz + kSgK - 1) / kSgK * kSgK;
+  return (K + kslice - 1) / kslice;
+}
+// y = sum_z part[z] + bias; emb = y / |y| (no epsilon, speech_embedder_net.py:32); one warp per row
+__global__ void __launch_bounds__(256) proj_finish_kernel(const float* __restrict__ part, int kz, const float* __restrict__ bias,
+                                                          float* __restrict__ y, float* __restrict__ inv_norm,
+                                                          float* __restrict__ emb, int B, int P) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float ss = 0.f;
+  for (int p = lane; p < P; p += 32) {
+    float v = bias[p];
+    for (int z = 0; z < kz; ++z) v += part[((size_t)z * B + b) * P + p];
+    y[(size_t)b * P + p] = v;
+    ss += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / sqrtf(ss);
+  for (int p = lane; p < P; p += 32) emb[(size_t)b * P + p] = y[(size_t)b * P + p] * inv;
+  if (lane == 0) inv_norm[b] = inv;
+}
+// out[c] = sum_r x[r, c]: 32 columns x 32 row lanes per CTA, fixed-order tree
+__global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, rl = threadIdx.y;
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = rl; r < rows; r += 32) acc += x[(size_t)r * cols + c];
+  red[rl][threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    out[c] = t;
+  }
 }
 __global__ void add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -498,13 +532,6 @@ __global__ void sumz_kernel(const float* __restrict__ part, float* __restrict__ 
   float acc = 0.f;
   for (int z = 0; z < kz; ++z) acc += part[(size_t)z * n + i];
   out[i] = acc;
-}
-__global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += x[(size_t)r * cols + c];
-  out[c] = acc;
 }
 // Column sums of dG [rows, 4H] (bf16, packed columns) -> partial sums per row chunk, then unpack + reduce.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
@@ -813,8 +840,9 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
     }
   }
   prof_mark(PH_PROJ, s);
-  proj_norm_kernel<<<(B + kProjRows - 1) / kProjRows, 256, (size_t)kProjRows * (H + P) * 4, s>>>(
-      w.h_last, proj_w, proj_b, w.y, w.inv_norm, emb, B, H, P);
+  // y = h_last W^T + b (split-K partials) -> bias, row norm, embedding
+  sgemm64(w.h_last, H, 1, proj_w, H, 1, w.proj_part, P, B, P, H, kProjSlices, s);
+  proj_finish_kernel<<<(B + 7) / 8, 256, 0, s>>>(w.proj_part, sgemm64_slices(H, kProjSlices), proj_b, w.y, w.inv_norm, emb, B, P);
   prof_mark(-1, s);
   SVB_CUDA("proj_norm");
   return SVB_OK;
@@ -835,9 +863,17 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   // ---- projection + norm backward (fp32)
   prof_mark(PH_PROJ_BWD, s);
   norm_bwd_kernel<<<(B + 7) / 8, 256, 0, s>>>(demb, w.y, w.inv_norm, w.dy, B, P);
-  sgemm_small(w.dy, w.h_last, grads[4 * L], P, H, B, 1, 0, s);          // dW_proj[P,H] = dy^T h_last
-  colsum_f32_kernel<<<(P + 127) / 128, 128, 0, s>>>(w.dy, grads[4 * L + 1], B, P);
-  sgemm_small(w.dy, proj_w, w.dh_last, B, H, P, 0, 0, s);               // dh_last[B,H] = dy W_proj
+  {   // dW_proj[P,H] = dy^T h_last (reduction over the batch split in two when it is long), db = column sums of dy
+    const int kz = B >= 256 ? 2 : 1;
+    const int nz = sgemm64_slices(B, kz);
+    float* dst = nz > 1 ? w.wg_tmp : grads[4 * L];       // (wg_tmp is free until the weight-gradient GEMMs)
+    sgemm64(w.dy, 1, P, w.h_last, 1, H, dst, H, P, H, B, kz, s);
+    if (nz > 1)
+      add2_kernel<<<148, 256, 0, s>>>(reinterpret_cast<const float4*>(w.wg_tmp), reinterpret_cast<const float4*>(w.wg_tmp + (size_t)P * H),
+                                      reinterpret_cast<float4*>(grads[4 * L]), (size_t)P * H / 4);
+  }
+  colsum_rows_kernel<<<(P + 31) / 32, dim3(32, 32), 0, s>>>(w.dy, grads[4 * L + 1], B, P);
+  sgemm64(w.dy, P, 1, proj_w, 1, H, w.dh_last, H, B, H, P, 1, s);       // dh_last[B,H] = dy W_proj
   SVB_CUDA("projection backward");
   bool use_wbptt = false, overlap = false;
   SideStream* side = nullptr;
