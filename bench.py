@@ -33,9 +33,6 @@ PHASES = ["prep", "input_gemm", "recurrent_fwd", "projection", "projection_bwd",
           "bias_grads", "dx"]
 
 
-PREWARM = 12
-
-
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -46,19 +43,67 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region.  NVML from a thread of this process (pynvml, the
+    library nvidia-smi itself uses): a looping nvidia-smi subprocess took ~200 ms per query on some boxes and stalled
+    kernel launches for tens of ms inside a timed loop.  Falls back to the nvidia-smi loop of the profiling recipe
+    (-lms 200) if pynvml is unavailable."""
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None, period=0.05):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.p, self.thread, self.stop_flag = None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {pynvml.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, n in names.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        self.source = "nvidia-smi -lms 200"
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = self.samples
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(self.reasons), "source": self.source}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -82,7 +127,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
 
 
 def launches_per_step(world):
@@ -391,14 +436,7 @@ def main():
             p.grad = None
         return fwd_bwd(x_dev)
 
-    # settle allocator, module loading and clocks before ANY timed loop (the first timed loop of a fresh process was
-    # 0.2-0.3 ms/step slower than the same loop run later); every timed loop still does its own W warm-up steps
-    for _ in range(PREWARM):
-        value_step()
-    for _ in range(3):
-        full_step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if rank == 0 else None
     ms_value = timed(value_step, args.steps, args.warmup)
     ms_e2e = timed(full_step, args.steps, args.warmup)
     # section 8(f) additions, opt-in for a caller: H2D of the next batch on a copy stream (staging.prefetch) and the
@@ -471,7 +509,6 @@ def main():
                                     "fp32 accumulate/cell state/loss",
                        "parallelism": f"dp{world} by speaker group" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (untimed)",
-                       "prewarm": f"{PREWARM} + 3 untimed steps before the first timed loop, then W warm-up steps per loop",
                        "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
             "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utts/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},

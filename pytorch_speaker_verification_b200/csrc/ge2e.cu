@@ -949,16 +949,30 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
         spk_smem_set[CL - 1][MP / 2 - 1] = (int)sm;
       }
       if (CL > 1) {
-        static unsigned* bar_tab[64] = {};
+        // barrier word per (device, stream): launches on one stream are serialised, launches on different streams
+        // may overlap and must not share a word (256 B apart: separate L2 lines)
+        struct BarSlot { int dev; cudaStream_t st; unsigned* word; };
+        static BarSlot slots[32];
+        static int nslots = 0;
+        static unsigned* pool[64] = {};
+        static int used[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev < 0 || dev >= 64) continue;
-        if (!bar_tab[dev]) {
-          if (cudaMalloc(&bar_tab[dev], 256) != cudaSuccess || cudaMemset(bar_tab[dev], 0, 256) != cudaSuccess) {
-            cudaGetLastError(); bar_tab[dev] = nullptr; cluster_ok = 0; continue;
+        unsigned* word = nullptr;
+        for (int i = 0; i < nslots; ++i)
+          if (slots[i].dev == dev && slots[i].st == s) word = slots[i].word;
+        if (!word) {
+          if (!pool[dev]) {
+            if (cudaMalloc(&pool[dev], 32 * 256) != cudaSuccess || cudaMemset(pool[dev], 0, 32 * 256) != cudaSuccess) {
+              cudaGetLastError(); pool[dev] = nullptr; cluster_ok = 0; continue;
+            }
           }
+          if (nslots >= 32 || used[dev] >= 32) continue;          // too many streams: single-CTA form
+          word = pool[dev] + 64 * used[dev]++;
+          slots[nslots++] = BarSlot{dev, s, word};
         }
-        a.bar = bar_tab[dev];
+        a.bar = word;
       }
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(kST); cfg.dynamicSmemBytes = sm; cfg.stream = s;
