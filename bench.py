@@ -33,6 +33,19 @@ PHASES = ["prep", "input_gemm", "recurrent_fwd", "projection", "projection_bwd",
           "bias_grads", "dx"]
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -327,7 +340,7 @@ def run_reference(args, rank):
                        "sample": sample},
             "cpu_baseline": {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -339,6 +352,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--recurrent-terms", type=int, default=1)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything libraries print to fd 1 meanwhile (NCCL's version
+    # banner, warnings) goes to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -536,7 +555,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             rate, sample, cores, _ = cpu_reference_rate(2, 1, budget_s=40.0)
             line["cpu_baseline"] = {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
