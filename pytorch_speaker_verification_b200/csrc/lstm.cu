@@ -645,6 +645,7 @@ static SideStream* side_stream() {
   return &ss;
 }
 #define SIDE_DBG(i, stream) do { if (side && side->dbg[i]) cudaEventRecord(side->dbg[i], stream); } while (0)
+static int g_wgrad_late_pct = 30;   // share of the frames whose weight-gradient slices run beside BPTT
 static int g_wgrad_overlap = getenv("SVB_WGRAD_OVERLAP") ? atoi(getenv("SVB_WGRAD_OVERLAP")) : 1;   // late-frame weight-gradient slices run beside the persistent BPTT kernel
 static Profiler g_prof;
 static int g_persistent = 1;   // persistent wavefront forward kernel (wlstm.cuh) when the shape allows
@@ -687,6 +688,7 @@ using namespace svb;
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
 extern "C" int svb_set_persistent_bwd(int on) { g_persistent_bwd = on != 0; return SVB_OK; }
 extern "C" int svb_set_wgrad_overlap(int on) { g_wgrad_overlap = on != 0; return SVB_OK; }
+extern "C" int svb_set_wgrad_late_pct(int pct) { g_wgrad_late_pct = pct < 1 ? 1 : pct > 90 ? 90 : pct; return SVB_OK; }
 // Debug (SVB_WGRAD_DEBUG=1): ms since the fork of the last backward: gate of the top layer open, side stream done,
 // BPTT kernel done, backward done.  Synchronises.
 extern "C" int svb_wgrad_overlap_timing(float* out4) {
@@ -951,7 +953,9 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     SVB_TRY(launch_wbptt<768>(bp, s));
     if (overlap) {
       SIDE_DBG(3, s);
-      t0 = T - (3 * T) / 10;                            // late frames [t0, T): ~30 % of the reduction
+      t0 = T - (g_wgrad_late_pct * T) / 100;            // late frames [t0, T): ~30 % of the reduction
+      if (t0 < 1) t0 = 1;
+      if (t0 > T - 1) t0 = T - 1;
       for (int l = L - 1; l >= 0; --l) {
         wait_frames_kernel<<<1, (nt + 31) / 32 * 32, 0, side->s>>>(w.dcnt + l * nt, nt, (unsigned)((H / 32) * (T - t0)));
         if (l == L - 1) SIDE_DBG(1, side->s);

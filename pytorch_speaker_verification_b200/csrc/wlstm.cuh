@@ -381,8 +381,11 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     for (int e = 0; e < 2; ++e) cx[e] = sub * 2048 + g * 128 + ((((unit >> 2) ^ ((e << 2) | g))) << 4) + (unit & 3) * 4;
     const uint32_t cin_a = smem_u32(cin) + buf * kWlCinBytes;
     const uint32_t hx = sub * 1024 + g * 64 + unit * 2;                // h tiles: row 4k + g -> hx + k * 256
-    for (long long it = grp; it < total; it += 2) {
-      const int t = (int)(it / nt), j = (int)(it % nt);
+    // (t, j) of tile `it` are carried along: a 64-bit it / nt and it % nt by a run-time divisor is a ~70-instruction
+    // subroutine call at the head of every tile's dependency chain
+    int t = grp / nt, j = grp % nt;
+    for (long long it = grp; it < total; it += 2, j += 2) {
+      while (j >= nt) { j -= nt; ++t; }
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       float4* gfrag = reinterpret_cast<float4*>(ly.gin) + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 2048 +
                       (size_t)sub * 512 + col;      // + ps * 1024 + k * 128 float4
@@ -509,10 +512,13 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
   } else if (warp == kWlWarpStore && !is_R) {
     // ------------------------------------------------------------------ signal warp (P): publish gin tiles
     if (lane == 0) {
-      for (long long it = 0; it < total; ++it) {
-        WL_ACC(w0, mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1)));
-        mbar_arrive(&gin_taken[it & 1]);
-        st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + (it % nt), (unsigned)(it / nt + 1));
+      long long it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int j = 0; j < nt; ++j, ++it) {
+          WL_ACC(w0, mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1)));
+          mbar_arrive(&gin_taken[it & 1]);
+          st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
+        }
       }
     }
   } else if (warp == kWlWarpStore && is_R) {
