@@ -36,6 +36,8 @@ constexpr int kWlStages = 3;           // operand ring: 3 x 6 x [64 rows x 64 K]
 constexpr int kWlKbBytes = kWlTile * 128;
 constexpr int kWlStageBytes = kWlKbPerStage * kWlKbBytes;
 constexpr int kWlGinRing = 3;          // frames of gin kept in flight per layer
+constexpr int kWlChunk = 16;           // tile order: chunks of 16 tiles, frame-major inside a chunk (see WL_FOR_TILES)
+constexpr int kWlGinLagMax = 24;       // ... and at most this many tiles (24 x 24 slices x 32 KB = 18 MB per layer: L2-resident)
 constexpr int kWlDeps = 4;             // tiles the dependency poller may run ahead
 constexpr int kWlEpiWarps = 16;        // four warps per TMEM lane quarter, 16 batch rows of the tile each
 // Warps 0..15 epilogue, 16 TMA producer, 17 MMA issuer, 18 store/signal, 19 dependency poller.  The single-thread
@@ -120,6 +122,26 @@ __device__ __forceinline__ void wait_two_counters(const unsigned* a, unsigned ta
       printf("svb: wlstm dependency timeout cta %d have (%u, %u) want (%u, %u)\n", blockIdx.x, va, vb, ta, tb);
       __trap();
     }
+  }
+}
+
+// Tile order of every role: the batch tiles are walked in chunks of kWlChunk, all T frames of a chunk before the next
+// chunk (a tail shorter than half a chunk is merged into the last one).  The dependencies are per tile, so any order
+// that keeps t ascending per tile is valid; this one keeps the live h / c / gin rows of a chunk in L2 when the batch
+// is large (extraction, EER: hundreds of tiles per frame ran 10 % slower per tile in plain frame-major order) and is
+// the plain frame-major order for nt <= 23.  `it` counts tiles in this order.
+__device__ __forceinline__ int wl_chunk_end(int jc, int nt) {
+  return (nt - (jc + kWlChunk) < kWlChunk / 2) ? nt : jc + kWlChunk;
+}
+#define WL_FOR_TILES(t, j, it)                                            \
+  for (int jc_ = 0, je_ = wl_chunk_end(0, nt); jc_ < nt; jc_ = je_, je_ = wl_chunk_end(jc_, nt)) \
+    for (int t = 0; t < T; ++t)                                           \
+      for (int j = jc_; j < je_; ++j, ++it)
+// one step of the same walk for code that carries (t, j) along
+__device__ __forceinline__ void wl_advance(int& t, int& j, int& jc, int& je, int T, int nt) {
+  if (++j == je) {
+    if (++t == T) { t = 0; jc = je; je = wl_chunk_end(jc, nt); }
+    j = jc;
   }
 }
 
@@ -219,9 +241,14 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // ------------------------------------------------------------------ dependency poller (runs ahead of the rest)
     // A satisfied poll still costs an L2 round trip (~1000 clk); here it overlaps the previous tiles' work.
     {
+      // P may run at most `lag` tiles ahead of its layer's recurrence: 3 frames is the capacity of the gin ring, but
+      // with a large batch (extraction: hundreds of tiles per frame) a producer that far ahead pushes every gin tile
+      // out of L2 before R reads it (80 GB of HBM traffic for 47 k windows); kWlGinLagMax tiles keep it resident.
+      const long long lag = (long long)kWlGinRing * nt < kWlGinLagMax ? (long long)kWlGinRing * nt : kWlGinLagMax;
+      int bt = 0, bj = 0, bjc = 0, bje = wl_chunk_end(0, nt);   // (frame, tile) of linear index it - lag
       long long it = 0;
-      for (int t = 0; t < T; ++t) {
-        for (int j = 0; j < nt; ++j, ++it) {
+      WL_FOR_TILES(t, j, it) {
+        {
           const int d = (int)(it % kWlDeps);
           WL_ACC(w0, mbar_wait(&dep_free[d], (uint32_t)(((it / kWlDeps) & 1) ^ 1)));
 #ifdef SVB_WL_ACCOUNT
@@ -232,8 +259,10 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
             wait_two_counters(t > 0 ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * t),
                               p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
           } else {
+            const bool bp = it >= lag;          // every R(l, .) has finished tile it - lag (and, in order, all before)
             wait_two_counters(l > 0 ? p.hcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (t + 1)),
-                              t >= kWlGinRing ? p.hcnt + l * nt + j : nullptr, (unsigned)(NS * (t - kWlGinRing + 1)));
+                              bp ? p.hcnt + l * nt + bj : nullptr, (unsigned)(NS * (bt + 1)));
+            if (bp) wl_advance(bt, bj, bjc, bje, T, nt);
           }
 #ifdef SVB_WL_ACCOUNT
           if (acct) w1 += clock64() - pa0;
@@ -248,8 +277,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // loads of later tiles, or load latency + MMA + epilogue chain up into the per-tile period.
     if (is_R) {
       long long it = 0;
-      for (int t = 0; t < T; ++t) {
-        for (int j = 0; j < nt; ++j, ++it) {
+      WL_FOR_TILES(t, j, it) {
+        {
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
           const int d = (int)(it % kWlDeps);
@@ -267,8 +296,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       long long it = 0;
-      for (int t = 0; t < T; ++t) {
-        for (int j = 0; j < nt; ++j, ++it) {
+      WL_FOR_TILES(t, j, it) {
+        {
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
           const int d = (int)(it % kWlDeps);
@@ -383,9 +412,9 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     const uint32_t hx = sub * 1024 + g * 64 + unit * 2;                // h tiles: row 4k + g -> hx + k * 256
     // (t, j) of tile `it` are carried along: a 64-bit it / nt and it % nt by a run-time divisor is a ~70-instruction
     // subroutine call at the head of every tile's dependency chain
-    int t = grp / nt, j = grp % nt;
-    for (long long it = grp; it < total; it += 2, j += 2) {
-      while (j >= nt) { j -= nt; ++t; }
+    int t = 0, j = 0, jc = 0, je = wl_chunk_end(0, nt);
+    if (grp) wl_advance(t, j, jc, je, T, nt);
+    for (long long it = grp; it < total; it += 2, wl_advance(t, j, jc, je, T, nt), wl_advance(t, j, jc, je, T, nt)) {
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       float4* gfrag = reinterpret_cast<float4*>(ly.gin) + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 2048 +
                       (size_t)sub * 512 + col;      // + ps * 1024 + k * 128 float4
@@ -513,8 +542,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // ------------------------------------------------------------------ signal warp (P): publish gin tiles
     if (lane == 0) {
       long long it = 0;
-      for (int t = 0; t < T; ++t) {
-        for (int j = 0; j < nt; ++j, ++it) {
+      WL_FOR_TILES(t, j, it) {
+        {
           WL_ACC(w0, mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1)));
           mbar_arrive(&gin_taken[it & 1]);
           st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
@@ -525,8 +554,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
     // ------------------------------------------------------------------ store + signal warp (R only)
     if (elect_one()) {
       long long it = 0;
-      for (int t = 0; t < T; ++t) {
-        for (int j = 0; j < nt; ++j, ++it) {
+      WL_FOR_TILES(t, j, it) {
+        {
           const int buf = (int)(it & 1);
           const uint32_t upar = (uint32_t)((it >> 1) & 1);
           WL_ACC(w0, mbar_wait(&stg_full[buf], upar));

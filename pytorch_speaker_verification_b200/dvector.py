@@ -124,23 +124,45 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
         return []
     nmels = int(specs[0].shape[0])
     Ts_all = np.asarray([int(s.shape[1]) for s in specs], dtype=np.int64)
-    # chunk boundaries by cumulative frames
-    bounds, acc = [0], 0
+    # chunk boundaries by cumulative frames; the first two chunks are smaller so that the GPU starts early
+    bounds, acc, target = [0], 0, max(1, chunk_frames // 4)
     for i, T in enumerate(Ts_all.tolist()):
         acc += T
-        if acc >= chunk_frames:
+        if acc >= target:
             bounds.append(i + 1)
             acc = 0
+            target = min(chunk_frames, target * 2)
     if bounds[-1] != n:
         bounds.append(n)
-    pending, held = [], []
+    pending = []          # per chunk: (pinned result view, D2H event, buffers) until harvested
+    counts_of = {}
+    res_chunks = [None] * (len(bounds) - 1)
+
+    def harvest(block):
+        """Copy finished chunks out of their page-locked buffers (one memcpy per chunk) and recycle the buffers;
+        non-blocking while later chunks are still being queued."""
+        for k, item in enumerate(pending):
+            if item is None:
+                continue
+            hv, ev, bufs = item
+            if hv is not None:
+                if not block and not ev.query():
+                    continue
+                if block:
+                    ev.synchronize()
+                res_chunks[k] = np.array(hv.numpy())
+                for t in bufs:
+                    _pool.give(t)
+            pending[k] = None
+
     with torch.cuda.device(dev):
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
+        for k, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
             Ts = Ts_all[lo:hi]
             F = int(Ts.sum())
             W, starts, seg, counts = _chunk_plan(Ts)
+            res_chunks[k] = counts                       # replaced by the data in harvest() when the chunk has windows
             if W == 0:
-                pending.append((None, 0, counts))
+                pending.append((None, None, ()))
                 continue
             # one staging buffer: [log-mel (nmels, F) float32 | starts int32 | seg int32]
             nb_spec, nb_st, nb_seg = nmels * F * 4, starts.size * 4, seg.size * 4
@@ -164,16 +186,20 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
             host = _pool.take(P * D * 8)
             hv = host[:P * D * 8].view(torch.float64).view(P, D)
             hv.copy_(out, non_blocking=True)
-            pending.append((hv, P, counts))
-            held += [stage, host]
-        torch.cuda.current_stream().synchronize()
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((hv, ev, (stage, host)))
+            counts_of[k] = counts
+            harvest(False)
+        harvest(True)
     res = []
-    for hv, P, counts in pending:
-        o = 0
-        arr = hv.numpy() if hv is not None else None
+    for k in range(len(res_chunks)):
+        counts = counts_of.get(k)
+        if counts is None:                                # chunk without any window
+            res.extend(np.zeros((0, D)) for _ in res_chunks[k])
+            continue
+        arr, o = res_chunks[k], 0
         for c in counts:
-            res.append(np.array(arr[o:o + c]) if c else np.zeros((0, D)))
+            res.append(arr[o:o + c] if c else np.zeros((0, D)))            # views of the chunk's array
             o += c
-    for t in held:
-        _pool.give(t)
     return res

@@ -311,6 +311,39 @@ def test_persistent_and_per_frame_kernels_agree(svb, net):
           "per-frame vs golden:", emb_err(out[False][0].cpu().numpy(), g["emb"]))
 
 
+@pytest.mark.parametrize("B,T", [(1540, 9), (1700, 6), (2100, 5), (3072, 4)])
+def test_persistent_forward_chunked_tile_order(svb, net, B, T):
+    """Batches of 24 or more 64-row tiles are walked in chunks of 16 tiles, all frames of a chunk before the next
+    chunk (merged tail, ragged last tile): every row must equal the row computed in a small batch (bit for bit: the
+    per-row arithmetic does not depend on the batch), inference and training forward, under a NaN-poisoned workspace;
+    and the training stash written in that order must give the per-frame path's gradients."""
+    from pytorch_speaker_verification_b200 import ops
+    x = torch.tensor(I.logmel(B, T, seed=B)).cuda()
+    try:
+        ops.set_poison_workspace(True)
+        with torch.no_grad():
+            big = net(x)
+            assert not torch.isnan(big).any()
+            for lo in (0, 960, 1024, B - 70):
+                assert torch.equal(net(x[lo:lo + 70]), big[lo:lo + 70]), lo
+        grads = {}
+        for mode in (True, False):
+            ops.set_persistent(mode)
+            ops.set_persistent_bwd(mode)
+            net.zero_grad()
+            e = net(x)
+            if mode:
+                assert torch.equal(e.detach(), big)
+            e.square().sum().mul(0.5).add(e.sum()).backward()
+            grads[mode] = [p.grad.clone() for p in net.parameters()]
+        for a, b in zip(grads[True], grads[False]):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-2
+    finally:
+        ops.set_poison_workspace(False)
+        ops.set_persistent(True)
+        ops.set_persistent_bwd(True)
+
+
 def test_persistent_bptt_matches_per_frame_bptt(svb, net):
     """The persistent wavefront BPTT kernel (split-K over 4-CTA clusters with a DSMEM reduction, dX products fused
     in) and the per-frame BPTT kernels + batched dX GEMMs consume the same stash and agree on every parameter
