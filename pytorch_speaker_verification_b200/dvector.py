@@ -79,7 +79,10 @@ class _PinnedPool:
                 best = i
         if best is not None:
             return self.free.pop(best)
-        return torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
+        size = 1 << 20                                   # power-of-two buckets: any later chunk of similar size fits
+        while size < nbytes:
+            size <<= 1
+        return torch.empty(size, dtype=torch.uint8).pin_memory()
 
     def give(self, t):
         self.free.append(t)
