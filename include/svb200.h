@@ -71,6 +71,14 @@ int svb_set_persistent(int on);
  * one cooperative cluster launch, split-K over 4-CTA clusters with a DSMEM reduction) when H == 768 and L <= 3;
  * 0 = one fused GEMM + gate-backward launch per frame and batched dX GEMMs. */
 int svb_set_persistent_bwd(int on);
+/* Weight gradients of the late frames beside the persistent BPTT kernel (csrc/lstm.cu): 1 (default; env
+ * SVB_WGRAD_OVERLAP=0 disables) = the products dW = dG^T X over the last `pct` percent of the frames run on a
+ * library-owned second stream, gated by the BPTT kernel's release counters, on the SMs it leaves idle; 0 = all
+ * weight-gradient GEMMs after it.  svb_wgrad_overlap_timing (SVB_WGRAD_DEBUG=1): ms since the fork of the last
+ * backward for {gate of the top layer open, side stream done, BPTT done, backward done}; synchronises. */
+int svb_set_wgrad_overlap(int on);
+int svb_set_wgrad_late_pct(int pct);
+int svb_wgrad_overlap_timing(float* out4);
 /* Debug hooks of the persistent kernels (timing experiments only): ablation mask (results become garbage) and
  * clock64 trace buffers (device pointers, or NULL). */
 int svb_set_ablate(int mask);
@@ -87,6 +95,9 @@ int svb_profile_read(float* ms_per_phase, int nphases);
 /* ---- GE2E loss (speech_embedder_net.py:35-49, utils.py:27-132) ---------------------------------------------------- */
 
 int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);
+/* Debug (env SVB_GE2E_TRACE=1): byte offset inside the workspace of the per-speaker kernel's clock64 phase stamps,
+ * [CTA][16] int64 (scripts/trace_ge2e.py). */
+int svb_ge2e_trace_offset(int N, int M, int D, int Nc, size_t* offset);
 
 /* One fused kernel for get_centroids + get_utterance_centroids + get_cossim (+ w*cos+b, calc_loss and all gradients).
  *   E (N,M,D); Cext (Nc,D) foreign centroids or NULL (centroids of E, Nc == N);

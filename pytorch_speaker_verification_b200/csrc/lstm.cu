@@ -612,7 +612,7 @@ __global__ void wait_frames_kernel(const unsigned* __restrict__ cnt, int nt, uns
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + j) : "memory");
     if (v >= target) break;
     if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 4000000000LL) {
+    else if (clock64() - t0 > 200000000000LL) {     // ~100 s: the gate legitimately waits for 70 % of a BPTT pass
       printf("svb: weight-gradient gate timeout tile %d have %u want %u\n", j, v, target);
       __trap();
     }
