@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvb200.so")
+LIB_PATH = os.environ.get("SVB_LIB_PATH") or os.path.join(_HERE, "libsvb200.so")   # (override: dev A/B builds)
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None

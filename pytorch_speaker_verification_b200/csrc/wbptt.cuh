@@ -28,8 +28,13 @@
 
 constexpr int kWbTile = 64;
 constexpr int kWbKb = 12;              // 64-wide K blocks per CTA (K slice of 768)
+#ifdef SVB_WB_ALT                      // experiment (make ALT=1 -> libsvb200_alt.so): finer, deeper operand ring
+constexpr int kWbKbPerStage = 2;       // 8 MMAs per barrier wait
+constexpr int kWbStages = 5;           // ring: 5 x 16 KB (a tile is 6 stages)
+#else
 constexpr int kWbKbPerStage = 3;       // 12 MMAs per barrier wait
 constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages)
+#endif
 constexpr int kWbStageBytes = kWbKbPerStage * kWbTile * 128;
 constexpr int kWbXRing = 3;
 constexpr int kWbDeps = 4;
