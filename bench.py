@@ -400,9 +400,19 @@ def main():
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    reducer = None
+    if world > 1 and os.environ.get("SVB_ALLREDUCE_OVERLAP", "0") == "1":
+        from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
+        reducer = OverlappedGradReducer()
+
     def fwd_bwd(x):
         emb = net(x)
         loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
+        if reducer is not None:               # SVB_ALLREDUCE_OVERLAP=1: bucketed all-reduce started from inside backward
+            with reducer:
+                loss.backward()
+            reducer.finish()
+            return loss
         loss.backward()
         if world > 1:
             allreduce_gradients(params)

@@ -62,6 +62,12 @@ int svb_embedder_forward(const void* x, int x_dtype, const void* packed, const f
 int svb_embedder_backward(const float* demb, const void* packed, const float* proj_w, float* const* grads,
                           void* workspace, int B, int T, int I, int H, int L, int P, void* stream);
 
+/* Host callback invoked by svb_embedder_backward as gradient buckets have been ENQUEUED on the caller's stream:
+ * bucket L = projection.weight/bias, then L-1 ... 0 = the four gradients of that LSTM layer (they are contiguous when
+ * the grads array points into one flat buffer in state_dict order).  A data-parallel caller starts that bucket's
+ * all-reduce immediately, overlapping it with the remaining weight-gradient GEMMs.  NULL clears it. */
+int svb_set_grad_ready_callback(void (*cb)(int bucket, void* user), void* user);
+
 /* LSTM forward path: 1 (default) = persistent wavefront kernel (csrc/wlstm.cuh: all layers and frames in one
  * cooperative launch, W_hh / W_ih slices stationary in tensor memory, fp16 operands, MUFU.TANH gates, tiles ordered by
  * release counters) when H is 256/512/768, L <= 3 and rec_terms == 1; 0 = batched input projection + one fused

@@ -628,6 +628,7 @@ __global__ void sum3_kernel(const float4* __restrict__ part, float4* __restrict_
 struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t layer_done[8] = {};     // late-frame slices of layer l are complete
   cudaEvent_t dbg[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // SVB_WGRAD_DEBUG: fork, gate open, side done, BPTT done, end
 };
 static SideStream* side_stream() {
@@ -639,6 +640,8 @@ static SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) { ss.s = nullptr; return nullptr; }
+    for (int i = 0; i < 8; ++i)
+      if (cudaEventCreateWithFlags(&ss.layer_done[i], cudaEventDisableTiming) != cudaSuccess) { ss.s = nullptr; return nullptr; }
     if (getenv("SVB_WGRAD_DEBUG"))
       for (int i = 0; i < 5; ++i) cudaEventCreate(&ss.dbg[i]);
   }
@@ -687,6 +690,16 @@ using namespace svb;
 // 1 (default): persistent recurrent forward kernel when the shape allows; 0: per-frame kernels everywhere.
 extern "C" int svb_set_persistent(int on) { g_persistent = on != 0; return SVB_OK; }
 extern "C" int svb_set_persistent_bwd(int on) { g_persistent_bwd = on != 0; return SVB_OK; }
+// Gradient-ready notification (host callback, called while svb_embedder_backward enqueues work): bucket = L for the
+// projection gradients, then L-1 ... 0 as each LSTM layer's four gradients have been enqueued on the caller's stream.
+// A data-parallel caller starts that bucket's all-reduce at once (dist.OverlappedGradReducer) instead of after the
+// whole backward.
+static void (*g_grad_cb)(int, void*) = nullptr;
+static void* g_grad_cb_user = nullptr;
+extern "C" int svb_set_grad_ready_callback(void (*cb)(int, void*), void* user) {
+  g_grad_cb = cb; g_grad_cb_user = user;
+  return SVB_OK;
+}
 extern "C" int svb_set_wgrad_overlap(int on) { g_wgrad_overlap = on != 0; return SVB_OK; }
 extern "C" int svb_set_wgrad_late_pct(int pct) { g_wgrad_late_pct = pct < 1 ? 1 : pct > 90 ? 90 : pct; return SVB_OK; }
 // Debug (SVB_WGRAD_DEBUG=1): ms since the fork of the last backward: gate of the top layer open, side stream done,
@@ -900,6 +913,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   colsum_rows_kernel<<<(P + 31) / 32, dim3(32, 32), 0, s>>>(w.dy, grads[4 * L + 1], B, P);
   sgemm64(w.dy, P, 1, proj_w, 1, H, w.dh_last, H, B, H, P, 1, s);       // dh_last[B,H] = dy W_proj
   SVB_CUDA("projection backward");
+  if (g_grad_cb) g_grad_cb(L, g_grad_cb_user);
   bool use_wbptt = false, overlap = false;
   SideStream* side = nullptr;
   int t0 = T;
@@ -962,6 +976,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         const size_t r0 = (size_t)t0 * B;
         SVB_TRY(wgrad_part(w.gates[l] + r0 * 4 * H, w.h_lo[l] + r0 * H, H, TB - (int)r0, 1, wg_slot(2 * l, 2), side->s));
         if (l > 0) SVB_TRY(wgrad_part(w.gates[l] + r0 * 4 * H, w.h_lo[l - 1] + BH + r0 * H, H, TB - (int)r0, 1, wg_slot(2 * l + 1, 2), side->s));
+        cudaEventRecord(side->layer_done[l], side->s);
       }
       cudaEventRecord(side->join, side->s);
       SIDE_DBG(2, side->s);
@@ -1100,16 +1115,18 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       }
       if (e != cudaSuccess) { set_error("dX", e); return SVB_ERR_CUDA; }
     }
-  }
-  if (overlap) {      // join: early slices (this stream) + late slices (side stream) -> gradients
-    prof_mark(PH_WGRAD, s);
-    cudaStreamWaitEvent(s, side->join, 0);
-    const size_t n4 = (size_t)4 * H * H / 4;
-    for (int l = 0; l < L; ++l) {
+    if (overlap) {    // join of this layer: early slices (this stream) + late slice (side stream, long finished)
+      prof_mark(PH_WGRAD, s);
+      cudaStreamWaitEvent(s, side->layer_done[l], 0);
+      const size_t n4 = (size_t)4 * H * H / 4;
       sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l, 0)), reinterpret_cast<float4*>(grads[4 * l + 1]), n4);
       if (l > 0) sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l + 1, 0)), reinterpret_cast<float4*>(grads[4 * l]), n4);
+      SVB_CUDA("weight gradient sums");
     }
-    SVB_CUDA("weight gradient sums");
+    if (g_grad_cb) g_grad_cb(l, g_grad_cb_user);        // all four gradients of layer l are enqueued
+  }
+  if (overlap) {
+    cudaStreamWaitEvent(s, side->join, 0);              // (already satisfied: joins the side stream for the next call)
     SIDE_DBG(4, s);
   }
   prof_mark(-1, s);

@@ -81,3 +81,41 @@ def allreduce_gradients(params, group=None):
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+class OverlappedGradReducer:
+    """SUM all-reduce of the embedder's gradients in four buckets (projection, then the LSTM layers from the top),
+    each started the moment its kernels are enqueued (svb_set_grad_ready_callback), so that the NCCL transfers run
+    beside the remaining weight-gradient GEMMs instead of after the whole backward::
+
+        reducer = OverlappedGradReducer()
+        with reducer:
+            loss.backward()
+        reducer.finish()            # the current stream waits for the four all-reduces
+
+    Every rank issues the same buckets in the same order (the order is fixed by the library)."""
+
+    def __init__(self, group=None, all_reduce=None):
+        self.group = group
+        self.works = []
+        self.buckets = 0
+        self._all_reduce = all_reduce or (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group,
+                                                                    async_op=True))
+
+    def _hook(self, bucket):
+        self.buckets += 1
+        self.works.append(self._all_reduce(bucket))
+
+    def __enter__(self):
+        ops.set_grad_bucket_hook(self._hook)
+        return self
+
+    def __exit__(self, *exc):
+        ops.set_grad_bucket_hook(None)
+        return False
+
+    def finish(self):
+        for w in self.works:
+            if w is not None:
+                w.wait()
+        self.works = []

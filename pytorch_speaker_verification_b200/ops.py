@@ -57,6 +57,17 @@ def set_wgrad_overlap(on):
     check(_lib.lib().svb_set_wgrad_overlap(int(bool(on))), "svb_set_wgrad_overlap")
 
 
+_GRAD_CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
+_bucket_hook = None
+
+
+def set_grad_bucket_hook(fn):
+    """fn(bucket: 1-D view of the flat gradient buffer) is called during backward as soon as a bucket's kernels are
+    enqueued on the current stream (projection first, then the LSTM layers from the top); None clears it."""
+    global _bucket_hook
+    _bucket_hook = fn
+
+
 def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
@@ -125,13 +136,33 @@ class EmbedderFn(torch.autograd.Function):
             dg = _stage(demb, torch.float32)
             # one flat buffer, parameters as views: a single all-reduce covers every gradient (dist.py)
             flat = torch.empty(sum(p.numel() for p in ctx.dev_params), dtype=torch.float32, device=dg.device)
-            grads, off = [], 0
+            grads, off, offs = [], 0, [0]
             for p in ctx.dev_params:
                 grads.append(flat[off:off + p.numel()].view(p.shape))
                 off += p.numel()
-            check(_lib.lib().svb_embedder_backward(ptr(dg), ptr(ctx.packed), ptr(ctx.dev_params[4 * L]),
-                                                   _ptr_array(grads), ptr(ctx.ws), B, T, I, H, L, P, stream_ptr()),
-                  "svb_embedder_backward")
+                offs.append(off)
+            cb, errors = None, []
+            if _bucket_hook is not None:
+                hook = _bucket_hook
+
+                def ready(bucket, _user):            # bucket L: projection, L-1 ... 0: LSTM layers (svb200.h)
+                    try:
+                        lo, hi = (offs[4 * L], offs[4 * L + 2]) if bucket == L else (offs[4 * bucket], offs[4 * bucket + 4])
+                        hook(flat[lo:hi])
+                    except BaseException as exc:         # exceptions cannot cross the C frame: re-raised below
+                        errors.append(exc)
+
+                cb = _GRAD_CB(ready)
+                check(_lib.lib().svb_set_grad_ready_callback(cb, None), "svb_set_grad_ready_callback")
+            try:
+                check(_lib.lib().svb_embedder_backward(ptr(dg), ptr(ctx.packed), ptr(ctx.dev_params[4 * L]),
+                                                       _ptr_array(grads), ptr(ctx.ws), B, T, I, H, L, P, stream_ptr()),
+                      "svb_embedder_backward")
+            finally:
+                if cb is not None:
+                    _lib.lib().svb_set_grad_ready_callback(None, None)
+            if errors:
+                raise errors[0]
         ctx.ws = None
         grads = [g if d.type == "cuda" else g.to(d) for g, d in zip(grads, ctx.param_devices)]
         return (None, None, None, *grads)

@@ -40,6 +40,21 @@ def _worker(rank, world, port, out):
     allreduce_gradients(list(net.parameters()))
     out[rank] = (loss.item(), net.LSTM_stack.weight_hh_l1.grad.cpu(), net.projection.weight.grad.cpu(),
                  crit.w.grad.item())
+    # the same step with the bucketed all-reduce started from inside backward: identical sums
+    from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
+    ref = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    crit.zero_grad()
+    emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
+    loss2 = GlobalGE2ELoss(crit)(emb.reshape(hi - lo, M, -1))
+    reducer = OverlappedGradReducer()
+    with reducer:
+        loss2.backward()
+    reducer.finish()
+    torch.cuda.synchronize()
+    assert reducer.buckets == 4
+    for p, r in zip(net.parameters(), ref):
+        assert torch.equal(p.grad, r), "bucketed all-reduce differs from the single all-reduce"
     dist.destroy_process_group()
 
 
