@@ -144,11 +144,15 @@ class ClockSampler:
 
 
 def launches_per_step(world):
-    fwd = 1 + 1 + 1                                    # prep, persistent wavefront LSTM kernel (all layers, all frames), projection
-    loss = 1                                           # fused GE2E (cooperative)
-    bwd = 1 + 4 + 1 + NLAYER * (2 + 2)                 # scale3, projection bwd, persistent BPTT (all layers, dX fused), per layer 2 wgrad + 2 bias
-    pack = NLAYER                                      # bf16 shadow refresh after the optimizer step
-    return fwd + loss + bwd + pack
+    """Our kernels per `value` step (fwd + GE2E + bwd), as listed by ncu in profiles/r1c_launches_step_summary.txt."""
+    fwd = 1 + 1 + 2                                    # prep_x, persistent wavefront LSTM kernel, projection GEMM + finish
+    loss = 1                                           # GE2E (per-speaker kernel; general kernel for the global batch)
+    bwd = (1 + 5 + 1                                   # scale3, projection bwd (norm, 2 GEMMs, add2, colsum), persistent BPTT
+           + NLAYER                                    # frame gates of the late weight-gradient slices
+           + 2 * (2 * NLAYER - 1)                      # early + late slices of the 5 wide weight-gradient products
+           + 2                                         # layer-0 dW_ih (N = 40) + its slice sum
+           + (2 * NLAYER - 1))                         # sum of the three partials per wide product
+    return fwd + loss + bwd
 
 
 def cpu_reference_rate(steps, warmup, budget_s=150.0):
