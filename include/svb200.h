@@ -167,6 +167,14 @@ int svb_dvector_windows(const float* S, int64_t ldS, int nmels, const int* win_s
 /* align_embeddings: out[p,:] = float64(mean over rows [seg_offsets[p], seg_offsets[p+1]) of emb (W,D) float32). */
 int svb_segment_mean(const float* emb, int D, const int* seg_offsets, int P, double* out, void* stream);
 
+/* ---- log-mel front end (data_preprocess.py:41-45, dvector_create.py:43-47) ----------
+ * PCM y (n float32 samples) -> out (nmels, n_frames) float32 = log10(mel_w . |STFT|^2 + 1e-6), n_frames = 1 + n/hop,
+ * n_fft = 512, librosa.core.stft framing (center=True, reflect padding).  window: 512 floats (the analysis window
+ * zero-padded to n_fft, non-zero on [w0, w1)); twiddle: 512 (cos, sin) pairs of 2 pi j / 512; mel_w: (nmels, 257).
+ * All tables are device pointers (pytorch_speaker_verification_b200/frontend.py builds them in float64). */
+int svb_logmel(const float* y, int64_t n, int hop, const float* window, int w0, int w1, const float* twiddle,
+               const float* mel_w, int nmels, float* out, int n_frames, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,3 +9,4 @@ from .eer import compute_eer, eer_sweep                              # noqa: F40
 from .dvector import align_embeddings, extract_dvectors, get_windows  # noqa: F401
 from .optim import FusedClipSGD                                       # noqa: F401
 from .staging import prefetch                                         # noqa: F401
+from .frontend import log_mel_spectrogram                              # noqa: F401

@@ -585,3 +585,29 @@ def test_full_size_c3_ge2e_and_c5_eer(svb):
     assert sim.shape == (1024, 3, 1024)
     assert [float(v) for v in tup] == [float(v) for v in oeer.eer_sweep(sim.cpu().numpy())]
     assert 0.0 < float(tup[0]) < 0.5
+
+
+# ----------------------------------------------------------------------------------------------- front end (8(f)-4)
+def test_log_mel_front_end_matches_oracle(svb, net):
+    """svb.log_mel_spectrogram (csrc/frontend.cu) against the float64 restatement of librosa's stft / filters.mel
+    (oracle/frontend.py; PARITY UNPINNED: librosa itself is not available).  Tolerance 2e-3 in log10 units on
+    speech-like signals (float32 direct DFT of 400 samples), frame count and reflect padding at both ends, and the
+    result feeds the extraction path."""
+    from oracle import frontend as ofe
+    r = np.random.RandomState(11)
+    for n in (16000, 24123, 400, 3 * 160 + 7):
+        t = np.arange(n) / 16000.0
+        y = (0.2 * np.sin(2 * np.pi * 220.0 * t) + 0.1 * np.sin(2 * np.pi * 3150.0 * t + 0.3)
+             + 0.05 * r.randn(n) * (0.2 + np.abs(np.sin(2 * np.pi * 1.5 * t)))).astype(np.float32)
+        S = svb.log_mel_spectrogram(y)
+        ref = ofe.log_mel(y.astype(np.float64))
+        assert S.shape == ref.shape == (40, 1 + n // 160)
+        err = np.abs(S.cpu().numpy().astype(np.float64) - ref).max()
+        assert err < 2e-3, (n, err)
+    silent = svb.log_mel_spectrogram(np.zeros(8000, dtype=np.float32))
+    assert torch.all(silent == -6.0)                                         # log10(0 + 1e-6)
+    with pytest.raises(ValueError):
+        svb.log_mel_spectrogram(np.zeros(200, dtype=np.float32))
+    S = svb.log_mel_spectrogram(0.1 * r.randn(24000).astype(np.float32))          # 151 frames -> 11 windows
+    out = svb.extract_dvectors(net, [S.cpu().numpy()])
+    assert out[0].shape[1] == 256 and out[0].shape[0] >= 1

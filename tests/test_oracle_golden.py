@@ -190,3 +190,29 @@ def test_optimizer_tail_closed_form_matches_library_calls():
     np.testing.assert_allclose(nl, nn_, rtol=1e-6)
     for a, b in zip(sum(pl, []) + sum(gl, []), sum(pn, []) + sum(gn, [])):
         np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7)
+
+
+def test_front_end_oracle_properties():
+    """oracle.frontend (PARITY UNPINNED, librosa absent): properties librosa documents -- hz_to_mel(8000) on the
+    Slaney scale, unit-area triangular filters, periodic Hann (sum N/2) centred in the n_fft frame, 1 + n//hop frames,
+    Parseval for a frame, and a pure tone landing in the mel band that contains its frequency."""
+    from oracle import frontend as ofe
+    assert abs(float(ofe.hz_to_mel(8000.0)) - 45.245640471924965) < 1e-9
+    assert abs(float(ofe.mel_to_hz(ofe.hz_to_mel(4321.0))) - 4321.0) < 1e-6
+    w = ofe.mel_filterbank()
+    assert w.shape == (40, 257) and w.min() >= 0.0
+    np.testing.assert_allclose(w.sum(axis=1) * (8000.0 / 256), 1.0, atol=0.06)      # area 1 in Hz (31.25 Hz bins)
+    win = ofe.hann_window_padded()
+    assert abs(win.sum() - 200.0) < 1e-9 and np.all(win[:56] == 0) and np.all(win[456:] == 0) and win[56] == 0.0
+    r = np.random.RandomState(2)
+    y = r.randn(1603)
+    P = ofe.stft_power(y)
+    assert P.shape == (257, 1 + 1603 // 160)
+    frame = np.pad(y, 256, mode="reflect")[5 * 160:5 * 160 + 512] * win
+    full = P[:, 5].sum() * 2 - P[0, 5] - P[256, 5]                                  # two-sided spectrum energy
+    assert abs(full / 512 - (frame ** 2).sum()) < 1e-9 * full
+    t = np.arange(8000) / 16000.0
+    S = ofe.log_mel(0.3 * np.sin(2 * np.pi * 1000.0 * t))
+    edges = ofe.mel_to_hz(np.linspace(ofe.hz_to_mel(0.0), ofe.hz_to_mel(8000.0), 42))
+    band = int(np.argmax(S[:, 20]))
+    assert edges[band] < 1000.0 < edges[band + 2]
