@@ -28,7 +28,7 @@
 
 constexpr int kWbTile = 64;
 constexpr int kWbKb = 12;              // 64-wide K blocks per CTA (K slice of 768)
-#ifdef SVB_WB_ALT                      // experiment (make ALT=1 -> libsvb200_alt.so): finer, deeper operand ring
+#ifdef SVB_WB_RING_ALT                 // experiment (make ALT=1 -> libsvb200_alt.so): finer, deeper operand ring
 constexpr int kWbKbPerStage = 2;       // 8 MMAs per barrier wait
 constexpr int kWbStages = 5;           // ring: 5 x 16 KB (a tile is 6 stages)
 #else
@@ -37,7 +37,11 @@ constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages)
 #endif
 constexpr int kWbStageBytes = kWbKbPerStage * kWbTile * 128;
 constexpr int kWbXRing = 3;
+#ifdef SVB_DEPS_ALT
+constexpr int kWbDeps = 8;
+#else
 constexpr int kWbDeps = 4;
+#endif
 constexpr int kWbEpiWarps = 16;
 constexpr int kWbThreads = 32 * kWbEpiWarps + 128;
 constexpr int kWbWarpTma = kWbEpiWarps, kWbWarpMma = kWbEpiWarps + 1, kWbWarpStore = kWbEpiWarps + 2,
