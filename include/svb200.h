@@ -123,6 +123,11 @@ int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, con
 int svb_centroids(const float* E, float* C, int N, int M, int D, void* stream);
 int svb_centroids_bwd(const float* dC, float* dE, int N, int M, int D, void* stream);
 
+/* utils.get_utterance_centroids (utils.py:40-58): U (N,M,D) = (sum over a speaker's utterances - the utterance itself)
+ * / (M - 1), float32 operations in the reference's order (bit-exact for D >= 16).  The operator is its own adjoint: the
+ * backward pass calls it on dL/dU. */
+int svb_utterance_centroids(const float* E, float* U, int N, int M, int D, void* stream);
+
 /* utils.calc_loss (utils.py:126-132) on a caller-supplied similarity matrix S (N,M,Nc); dS optional. */
 int svb_calc_loss(const float* S, int N, int M, int Nc, float* per_out, float* loss_out, float* dS,
                   const float* gscale, void* stream);

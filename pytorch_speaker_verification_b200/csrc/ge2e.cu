@@ -14,6 +14,7 @@
 //   D  per speaker : dE += dC_j/M + leave-one-out chain; block 0 reduces loss, dw, db deterministically
 // Reductions are warp shuffles + fixed-order shared-memory trees (no float atomics -> run-to-run identical).
 #include "../../include/svb200.h"
+#include "perdev.cuh"
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -913,12 +914,10 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   const size_t smem = smem_bytes(a);
   if (smem > 200 * 1024) { set_error("svb_ge2e: M*D too large for one CTA's shared memory", cudaSuccess); return SVB_ERR_UNSUPPORTED; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static int max_smem_set = 0, num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int max_smem_tab[kMaxDevices] = {};          // cudaFuncSetAttribute is per device
+  const int dev_i = current_device_index();
+  int& max_smem_set = max_smem_tab[dev_i];
+  const int num_sms = device_sm_count();
   if ((int)smem > max_smem_set) {
     cudaError_t e = cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -942,7 +941,8 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
       const size_t sm = spk_layout(N, D / CL, MP).floats * sizeof(float);
       if (sm > 220 * 1024) break;
       void* fn = spk_kernel(MP, CL);
-      static int spk_smem_set[2][kSpkMaxM / 2] = {};
+      static int spk_smem_tab[kMaxDevices][2][kSpkMaxM / 2] = {};
+      int (&spk_smem_set)[2][kSpkMaxM / 2] = spk_smem_tab[dev_i];
       if ((int)sm > spk_smem_set[CL - 1][MP / 2 - 1]) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute (speaker kernel)", e); return SVB_ERR_CUDA; }
@@ -1013,14 +1013,47 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
   return SVB_OK;
 }
 
+// Sum over the utterance axis in the order torch's CPU sum kernel uses for this layout (reduction over a strided
+// dimension with a contiguous inner dimension of at least one SIMD vector: ATen SumKernel.cpp, cascade summation):
+// rows are added sequentially into a level-0 accumulator that is flushed into level 1 every 16 rows, level 1 into
+// level 2 every 256, level 2 into level 3 every 4096; remaining rows go to level 0 and the levels are added in order.
+// For M < 16 (every batch shape the reference uses) this is the plain sequential sum.  Bit-exact against the
+// reference's `embeddings.sum(dim=1)` / `.mean(dim=1)` for D >= 16 (tests/golden/centroids.npz).
+__device__ __forceinline__ float cascade_sum_rows(const float* __restrict__ x, int M, size_t stride) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = 0;
+  for (; i + 16 <= M;) {
+    for (int j = 0; j < 16; ++j, ++i) a0 = __fadd_rn(a0, x[(size_t)i * stride]);
+    a1 = __fadd_rn(a1, a0); a0 = 0.f;
+    if ((i & 0xf0) == 0) {
+      a2 = __fadd_rn(a2, a1); a1 = 0.f;
+      if ((i & 0xf00) == 0) { a3 = __fadd_rn(a3, a2); a2 = 0.f; }
+    }
+  }
+  for (; i < M; ++i) a0 = __fadd_rn(a0, x[(size_t)i * stride]);
+  a0 = __fadd_rn(a0, a1);
+  a0 = __fadd_rn(a0, a2);
+  return __fadd_rn(a0, a3);
+}
 // get_centroids (utils.py:27-29): C[j, d] = mean_m E[j, m, d]; backward: dE[j, m, d] = dC[j, d] / M.
 __global__ void centroid_kernel(const float* __restrict__ E, float* __restrict__ C, int N, int M, int D) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * D) return;
   const int j = i / D, d = i % D;
-  float acc = 0.f;
-  for (int m = 0; m < M; ++m) acc += E[((size_t)j * M + m) * D + d];
-  C[i] = acc / (float)M;
+  C[i] = __fdiv_rn(cascade_sum_rows(E + (size_t)j * M * D + d, M, D), (float)M);
+}
+// get_utterance_centroids (utils.py:40-58): U[j, i, :] = (sum_m E[j, m, :] - E[j, i, :]) / (M - 1), the same three
+// float32 operations (sum over dim 1, subtract, divide) in the same order.  The operator is linear and symmetric, so
+// its backward is the same kernel applied to dL/dU.
+__global__ void utterance_centroid_kernel(const float* __restrict__ E, float* __restrict__ U, int N, int M, int D) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * D) return;
+  const int j = i / D, d = i % D;
+  const float* e = E + (size_t)j * M * D + d;
+  const float s = cascade_sum_rows(e, M, D);
+  const float den = (float)(M - 1);
+  float* u = U + (size_t)j * M * D + d;
+  for (int m = 0; m < M; ++m) u[(size_t)m * D] = __fdiv_rn(__fsub_rn(s, e[(size_t)m * D]), den);
 }
 __global__ void centroid_bwd_kernel(const float* __restrict__ dC, float* __restrict__ dE, int N, int M, int D) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1033,6 +1066,12 @@ extern "C" int svb_centroids(const float* E, float* C, int N, int M, int D, void
   if (!E || !C || N < 1 || M < 1 || D < 1) return SVB_ERR_ARG;
   const size_t n = (size_t)N * D;
   centroid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(E, C, N, M, D);
+  return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
+}
+extern "C" int svb_utterance_centroids(const float* E, float* U, int N, int M, int D, void* stream) {
+  if (!E || !U || N < 1 || M < 2 || D < 1) { set_error("svb_utterance_centroids: bad argument (M must be >= 2)", cudaSuccess); return SVB_ERR_ARG; }
+  const size_t n = (size_t)N * D;
+  utterance_centroid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(E, U, N, M, D);
   return cudaGetLastError() == cudaSuccess ? SVB_OK : SVB_ERR_CUDA;
 }
 extern "C" int svb_centroids_bwd(const float* dC, float* dE, int N, int M, int D, void* stream) {

@@ -10,8 +10,8 @@
 //   hseq[l]   [T+1, B, H]  fp16 + bf16    h_t in slot t+1, slot 0 = h_{-1} = 0 (fp16: forward operand; bf16: operand
 //                                         of the weight-gradient GEMMs next to the bf16 dG)
 //   cseq[l]   [T+1, B, H]  fp32           c_t in slot t+1 (training; 2 slots otherwise)
-//   gates[l]  [T+1, B, 4H] bf16           sigma/tanh gate activations (training), overwritten in place by the
-//                                         gate pre-activation gradients dG during BPTT; slot T = 0
+//   gates[l]  [T+1, B, 4H] 16-bit         sigma/tanh gate activations as fp16 (training), overwritten in place by the
+//                                         gate pre-activation gradients dG as bf16 during BPTT; slot T = 0
 // Packed gate order: column p = 32*(u/8) + 8*g + (u%8) for gate g in (i,f,g,o) of hidden unit u, so every
 // 32-column accumulator chunk that an epilogue thread owns holds all four gates of 8 units and the cell update
 // is fused into the recurrent GEMM's epilogue with no exchange between threads.
@@ -120,6 +120,7 @@ struct Work {
   float *h_last, *y, *inv_norm;     // [B,H], [B,P], [B]
   float* proj_part;                 // [kProjSlices][B,P] split-K partials of the projection
   float *dh_above, *dc, *dh_last, *dy;  // backward: [T,B,H], [B,H], [B,H], [B,P]
+  float* gscale;                    // backward: {s, 1/s}, the power-of-two scale BPTT runs under (grad_scale_kernel)
   float* dcl[8];                    // persistent BPTT: running dL/dc per layer [B,H]
   float* xring[8];                  // persistent BPTT: dX ring of layer l >= 1, [3][nt][H/32][64 x 32] fp32
   unsigned *dcnt, *xcnt;            // persistent BPTT progress counters [L][nt], [L][H/32][nt]
@@ -166,6 +167,7 @@ static Work layout_work(char* base, const Dims& d, int training) {
     w.dc = (float*)take(B * H * 4);
     w.dh_last = (float*)take(B * H * 4);
     w.dy = (float*)take(B * d.P * 4);
+    w.gscale = (float*)take(256);
     w.colsum_part = (float*)take(((T * B + kColsumRows - 1) / kColsumRows) * 4 * H * 4);
     const size_t nt = (B + 63) / 64, NS = H / 32;
     for (int l = 0; l < d.L; ++l) {
@@ -226,6 +228,15 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Gate stash format: fp16.  The activations lie in [-1, 1], where fp16 keeps 11 significant bits against bf16's 8;
+// the derivative factors s (1 - s) and 1 - g^2 formed from bf16-rounded activations were the largest error of the
+// parameter gradients (scripts/precision_study_bwd.py: bias gradients 2-8e-2 -> 0.8-2e-2, weights 1.4e-2 -> 7e-3).
+// The same buffer is overwritten in place by dG in bf16 (gradient range), the operand format of the BPTT GEMMs.
+__device__ __forceinline__ uint4 pack8_stash(const float (&v)[8]) {
+  return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+}
+__device__ __forceinline__ float stash_lo_of(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float stash_hi_of(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
 // h_t in both operand formats: fp16 (forward GEMMs) and bf16 (weight-gradient GEMMs)
 __device__ __forceinline__ void split_h8(const float (&hn)[8], uint4& hi, uint4& lo) {
   uint32_t hh[4], hl[4];
@@ -285,10 +296,10 @@ struct EpiLstmFwd {
     *reinterpret_cast<uint4*>(out + kOlo + row * 64 + c * 16) = lo;
     uint8_t* og = out + kOg + (c >> 1) * 16384;
     const int ub = (c & 1) * 4;
-    *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8(r.gi);
-    *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8(r.gf);
-    *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8(r.gg);
-    *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8(r.go);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 0)) = pack8_stash(r.gi);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 1)) = pack8_stash(r.gf);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 2)) = pack8_stash(r.gg);
+    *reinterpret_cast<uint4*>(og + sw128(row, ub + 3)) = pack8_stash(r.go);
     if (p.h_f32 && valid) {
       float* d = p.h_f32 + (size_t)m * p.H + (n0 >> 2) + 8 * c;
       *reinterpret_cast<float4*>(d) = make_float4(r.hn[0], r.hn[1], r.hn[2], r.hn[3]);
@@ -336,8 +347,8 @@ struct EpiLstmBwd {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
   static __device__ __forceinline__ void unpack8(uint4 w, float (&v)[8]) {
-    v[0] = bf16_lo_of(w.x); v[1] = bf16_hi_of(w.x); v[2] = bf16_lo_of(w.y); v[3] = bf16_hi_of(w.y);
-    v[4] = bf16_lo_of(w.z); v[5] = bf16_hi_of(w.z); v[6] = bf16_lo_of(w.w); v[7] = bf16_hi_of(w.w);
+    v[0] = stash_lo_of(w.x); v[1] = stash_hi_of(w.x); v[2] = stash_lo_of(w.y); v[3] = stash_hi_of(w.y);
+    v[4] = stash_lo_of(w.z); v[5] = stash_hi_of(w.z); v[6] = stash_lo_of(w.w); v[7] = stash_hi_of(w.w);
   }
   // one group of 8 hidden units (q = 0..3 within the CTA's 32 units); dh8 = recurrent part of dL/dh for them
   static __device__ __forceinline__ void apply_q(const Params& p, const uint8_t* in, uint8_t* out, int row, int q,
@@ -542,18 +553,62 @@ __global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restri
     out[c] = t;
   }
 }
-__global__ void add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, size_t n4) {
+// Gradient scale.  BPTT runs on dL/dh_last * s with s = 2^-floor(log2(max |dL/dh_last|)): bf16 dG operands are scale
+// free, but the fp16 split-K partials of the persistent BPTT kernel (and any future fp16 operand) are not -- a trained
+// model's gradients (loss ~ 0.4, |dL/dh| ~ 1e-5) would sit in the fp16 subnormals, a SUM loss over thousands of rows
+// grows the other way.  Under the scale every backward sees max |dL/dh_last| in [1, 2), so the result is the same
+// function of the gradient's DIRECTION whatever its magnitude; the kernels that finish a parameter gradient multiply
+// by 1/s (`inv`, exact: powers of two).  One block: 2 passes over B x H floats that the projection backward just wrote.
+__global__ void __launch_bounds__(1024) grad_scale_kernel(float* __restrict__ dh, size_t n, float* __restrict__ gscale) {
+  __shared__ float red[32];
+  __shared__ float s_sh;
+  float m = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(dh[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      float sc = 1.f;
+      if (m > 0.f && m < 3.0e38f) {            // (zero, inf or NaN gradients: unscaled)
+        int e = ilogbf(m);
+        e = e < -100 ? -100 : e > 100 ? 100 : e;
+        sc = ldexpf(1.f, -e);
+      }
+      s_sh = sc;
+      gscale[0] = sc;
+      gscale[1] = 1.f / sc;
+    }
+  }
+  __syncthreads();
+  const float sc = s_sh;
+  if (sc != 1.f)
+    for (size_t i = threadIdx.x; i < n; i += 1024) dh[i] *= sc;
+}
+__global__ void scale_inplace_kernel(float4* __restrict__ x, size_t n4, const float* __restrict__ inv) {
+  const float k = __ldg(inv);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 x = a[i], y = b[i];
-    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    float4 v = x[i];
+    x[i] = make_float4(v.x * k, v.y * k, v.z * k, v.w * k);
   }
 }
-__global__ void sumz_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n, int kz) {
+// (inv: device scalar multiplying the sum, or null)
+__global__ void add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, size_t n4,
+                            const float* __restrict__ inv) {
+  const float k = inv ? __ldg(inv) : 1.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4((x.x + y.x) * k, (x.y + y.y) * k, (x.z + y.z) * k, (x.w + y.w) * k);
+  }
+}
+__global__ void sumz_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n, int kz, const float* __restrict__ inv) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
   for (int z = 0; z < kz; ++z) acc += part[(size_t)z * n + i];
-  out[i] = acc;
+  out[i] = acc * (inv ? __ldg(inv) : 1.f);
 }
 // Column sums of dG [rows, 4H] (bf16, packed columns) -> partial sums per row chunk, then unpack + reduce.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part,
@@ -576,11 +631,12 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   for (int j = 0; j < 8; ++j) part[(size_t)blockIdx.y * cols + c + j] = a[j];
 }
 __global__ void bias_grad_finish_kernel(const float* __restrict__ part, int chunks, int H, float* __restrict__ g_ih,
-                                        float* __restrict__ g_hh) {
+                                        float* __restrict__ g_hh, const float* __restrict__ inv) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= 4 * H) return;
   float acc = 0.f;
   for (int c = 0; c < chunks; ++c) acc += part[(size_t)c * 4 * H + p];
+  acc *= __ldg(inv);
   const int r = ((p & 31) >> 3) * H + (p >> 5) * 8 + (p & 7);
   g_ih[r] = acc;       // b_ih and b_hh enter the pre-activation as a sum: identical gradients
   g_hh[r] = acc;
@@ -619,10 +675,11 @@ __global__ void wait_frames_kernel(const unsigned* __restrict__ cnt, int nt, uns
     __nanosleep(2000);
   }
 }
-__global__ void sum3_kernel(const float4* __restrict__ part, float4* __restrict__ out, size_t n4) {
+__global__ void sum3_kernel(const float4* __restrict__ part, float4* __restrict__ out, size_t n4, const float* __restrict__ inv) {
+  const float k = __ldg(inv);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = part[i], b = part[n4 + i], c = part[2 * n4 + i];
-    out[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+    out[i] = make_float4((a.x + b.x + c.x) * k, (a.y + b.y + c.y) * k, (a.z + b.z + c.z) * k, (a.w + b.w + c.w) * k);
   }
 }
 struct SideStream {
@@ -784,8 +841,7 @@ extern "C" int svb_embedder_forward(const void* x, int x_dtype, const void* pack
   }
   bool use_wlstm = false;
   if (g_persistent && rec_terms == 1 && L <= 3 && (H == 768 || H == 512 || H == 256)) {
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int num_sms = device_sm_count();
     use_wlstm = 2 * L * (H / 32) <= num_sms;
   }
   if (use_wlstm) {
@@ -908,10 +964,15 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     sgemm64(w.dy, 1, P, w.h_last, 1, H, dst, H, P, H, B, kz, s);
     if (nz > 1)
       add2_kernel<<<148, 256, 0, s>>>(reinterpret_cast<const float4*>(w.wg_tmp), reinterpret_cast<const float4*>(w.wg_tmp + (size_t)P * H),
-                                      reinterpret_cast<float4*>(grads[4 * L]), (size_t)P * H / 4);
+                                      reinterpret_cast<float4*>(grads[4 * L]), (size_t)P * H / 4, nullptr);
   }
   colsum_rows_kernel<<<(P + 31) / 32, dim3(32, 32), 0, s>>>(w.dy, grads[4 * L + 1], B, P);
   sgemm64(w.dy, P, 1, proj_w, 1, H, w.dh_last, H, B, H, P, 1, s);       // dh_last[B,H] = dy W_proj
+  grad_scale_kernel<<<1, 1024, 0, s>>>(w.dh_last, BH, w.gscale);       // BPTT runs on dh_last * 2^k, max in [1, 2)
+  const float* inv_scale = w.gscale + 1;
+  auto unscale = [&](float* g, size_t n) {                             // gradients stored directly by a GEMM epilogue
+    scale_inplace_kernel<<<148 * 2, 256, 0, s>>>(reinterpret_cast<float4*>(g), n / 4, inv_scale);
+  };
   SVB_CUDA("projection backward");
   if (g_grad_cb) g_grad_cb(L, g_grad_cb_user);
   bool use_wbptt = false, overlap = false;
@@ -935,8 +996,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     return SVB_OK;
   };
   if (g_persistent_bwd && H == 768 && L <= 3) {
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int num_sms = device_sm_count();
     use_wbptt = 4 * (2 * L - 1) * (H / 128) + 16 <= num_sms;    // clusters of 4 strand up to 16 SMs
   }
   if (use_wbptt) {
@@ -954,7 +1014,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       ly.gbias_ih = grads[4 * l + 2]; ly.gbias_hh = grads[4 * l + 3];
       cudaMemsetAsync(w.dcl[l], 0, BH * 4, s);
     }
-    bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last;
+    bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last; bp.inv_scale = inv_scale;
     bp.trace = reinterpret_cast<long long*>(g_trace_bwd);
     bp.B = B; bp.T = T; bp.L = L; bp.H = H; bp.nt = nt;
     cudaMemsetAsync(w.dcnt, 0, w.bcnt_bytes, s);
@@ -1024,16 +1084,16 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       // and ran at 67 % of the tensor peak); the 36 pair tiles of a 3072 x 768 product fill the machine only with the
       // reduction split in two (gridDim.z), the halves are summed by a streaming kernel
       const bool split2 = (H % 256 == 0) && TB >= 256;
-      auto wgrad_split2 = [&](GemmOperands& gg, float* out, int N) -> int {
+      auto wgrad_split2 = [&](GemmOperands& gg, float* out, int N, float* tmp) -> int {
         gg.kz = 2; gg.K = ((TB + 1) / 2 + 63) / 64 * 64;    // slice 1 runs past T*B: the TMA zero-fills out-of-range rows
         EpiStoreF32<256>::Params ep;
-        SVB_TRY(make_store_params<256>(&ep, w.wg_tmp, nullptr, 4 * H, N, (int64_t)N, H));
+        SVB_TRY(make_store_params<256>(&ep, tmp, nullptr, 4 * H, N, (int64_t)N, H));
         ep.z_stride = (int64_t)4 * H * N;
         cudaError_t ee = launch_tc_gemm<256, 6, true, true, EpiStoreF32<256>, 8, 1, true>(gg, ep, s);
         if (ee != cudaSuccess) { set_error("weight gradient (split-K pair tiles)", ee); return SVB_ERR_CUDA; }
         const size_t n4 = (size_t)4 * H * N / 4;
-        add2_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(w.wg_tmp), reinterpret_cast<const float4*>(w.wg_tmp + 4 * (size_t)H * N),
-                                           reinterpret_cast<float4*>(out), n4);
+        add2_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(tmp), reinterpret_cast<const float4*>(tmp + 4 * (size_t)H * N),
+                                           reinterpret_cast<float4*>(out), n4, inv_scale);
         gg.kz = 0; gg.K = TB;
         return SVB_OK;
       };
@@ -1041,16 +1101,18 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         SVB_TRY(wgrad_part(w.gates[l], w.h_lo[l], H, t0 * B, 2, wg_slot(2 * l, 0), s));
         e = cudaSuccess;
       } else if (split2) {
-        SVB_TRY(wgrad_split2(g, grads[4 * l + 1], H));
+        SVB_TRY(wgrad_split2(g, grads[4 * l + 1], H, w.wg_tmp));
         e = cudaSuccess;
       } else if (H % 128 == 0) {     // CTA pairs, 256 x 128 pair tiles (72 pairs = 144 CTAs at 4H x H = 3072 x 768)
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
         e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep, s);
+        unscale(grads[4 * l + 1], (size_t)4 * H * H);
       } else {
         EpiStoreF32<128>::Params ep;
         SVB_TRY(make_store_params<128>(&ep, grads[4 * l + 1], nullptr, 4 * H, H, (int64_t)H, H));
         e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep, s);
+        unscale(grads[4 * l + 1], (size_t)4 * H * H);
       }
       if (e != cudaSuccess) { set_error("dW_hh", e); return SVB_ERR_CUDA; }
       g.N = lw.I;
@@ -1058,13 +1120,16 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       if (overlap && l > 0) {
         SVB_TRY(wgrad_part(w.gates[l], xin, H, t0 * B, 2, wg_slot(2 * l + 1, 0), s));
         e = cudaSuccess;
-      } else if (split2 && lw.I % 256 == 0) {
-        SVB_TRY(wgrad_split2(g, grads[4 * l], lw.I));
+      } else if (split2 && lw.I % 256 == 0 && lw.I <= H) {
+        // (with the overlap on, slots 0..2 of product 0 hold the dW_hh partials of this layer until sum3 below:
+        //  layer 0's dW_ih partials go to the free slots of product 1)
+        SVB_TRY(wgrad_split2(g, grads[4 * l], lw.I, overlap ? wg_slot(1, 0) : w.wg_tmp));
         e = cudaSuccess;
       } else if (lw.I % 128 == 0) {
         EpiStoreF32<128>::Params ep2;
         SVB_TRY(make_store_params<128>(&ep2, grads[4 * l], nullptr, 4 * H, lw.I, (int64_t)lw.I, H));
         e = launch_tc_gemm<128, 8, true, true, EpiStoreF32<128>, 4, 1, true>(g, ep2, s);
+        unscale(grads[4 * l], (size_t)4 * H * lw.I);
       } else {
         // narrow input (layer 0: N = 40): only 4H/128 = 24 output tiles, so the reduction over T*B is split over
         // gridDim.z (144 CTAs at 4H = 3072) and the partial products are summed by a streaming kernel
@@ -1080,8 +1145,10 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
         e = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep2, s);
         if (kz > 1 && e == cudaSuccess) {
           const size_t n = (size_t)4 * H * lw.I;
-          sumz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(narrow_tmp, grads[4 * l], n, kz);
+          sumz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(narrow_tmp, grads[4 * l], n, kz, inv_scale);
           g.kz = 0; g.K = TB;
+        } else if (e == cudaSuccess) {
+          unscale(grads[4 * l], (size_t)4 * H * lw.I);
         }
       }
       if (e != cudaSuccess) { set_error("dW_ih", e); return SVB_ERR_CUDA; }
@@ -1091,7 +1158,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       const int chunks = (TB + kColsumRows - 1) / kColsumRows;
       dim3 grid((4 * H / 8 + 255) / 256, chunks);
       colsum_bf16_kernel<<<grid, 256, 0, s>>>(w.gates[l], w.colsum_part, TB, 4 * H);
-      bias_grad_finish_kernel<<<(4 * H + 255) / 256, 256, 0, s>>>(w.colsum_part, chunks, H, grads[4 * l + 2], grads[4 * l + 3]);
+      bias_grad_finish_kernel<<<(4 * H + 255) / 256, 256, 0, s>>>(w.colsum_part, chunks, H, grads[4 * l + 2], grads[4 * l + 3], inv_scale);
       SVB_CUDA("bias grads");
     }
     // ---- gradient w.r.t. the layer input = dh_above of the layer below: dX[T*B, H] = dG W_ih
@@ -1119,8 +1186,8 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
       prof_mark(PH_WGRAD, s);
       cudaStreamWaitEvent(s, side->layer_done[l], 0);
       const size_t n4 = (size_t)4 * H * H / 4;
-      sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l, 0)), reinterpret_cast<float4*>(grads[4 * l + 1]), n4);
-      if (l > 0) sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l + 1, 0)), reinterpret_cast<float4*>(grads[4 * l]), n4);
+      sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l, 0)), reinterpret_cast<float4*>(grads[4 * l + 1]), n4, inv_scale);
+      if (l > 0) sum3_kernel<<<148 * 4, 256, 0, s>>>(reinterpret_cast<const float4*>(wg_slot(2 * l + 1, 0)), reinterpret_cast<float4*>(grads[4 * l]), n4, inv_scale);
       SVB_CUDA("weight gradient sums");
     }
     if (g_grad_cb) g_grad_cb(l, g_grad_cb_user);        // all four gradients of layer l are enqueued

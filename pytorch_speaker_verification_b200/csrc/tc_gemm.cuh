@@ -347,11 +347,10 @@ template <int BN, int kStages, bool A_MN, bool B_MN, class Epi, int kEpiWarps = 
 cudaError_t launch_tc_gemm(const GemmOperands& ops, const typename Epi::Params& ep, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages, Epi, KSPLIT, TWO_CTA>;
   auto kern = tc_gemm_kernel<BN, kStages, A_MN, B_MN, Epi, kEpiWarps, KSPLIT, TWO_CTA>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;        // one bit per device
+  if (first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

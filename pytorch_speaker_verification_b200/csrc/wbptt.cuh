@@ -75,7 +75,8 @@ struct __align__(64) WbParams {
   WbLayer layer[3];
   unsigned* dcnt;          // [L][nt]
   unsigned* xcnt;          // [L][H/32][nt]
-  const float* dh_last;    // [B][H] dL/dh of the top layer's last frame
+  const float* dh_last;    // [B][H] dL/dh of the top layer's last frame (times the gradient scale, lstm.cu)
+  const float* inv_scale;  // device scalar: 1 / gradient scale, applied to the bias gradients on the way out
   long long* trace;
   int B, T, L, H, nt;
 };
@@ -502,10 +503,11 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
             const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
             const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcs[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
             float gi[4], gf[4], gg[4], go[4], di[4], df[4], dg[4], dO[4], dcn[4];
-            gi[0] = bf16_lo_of(gq[0].x); gi[1] = bf16_hi_of(gq[0].x); gi[2] = bf16_lo_of(gq[0].y); gi[3] = bf16_hi_of(gq[0].y);
-            gf[0] = bf16_lo_of(gq[1].x); gf[1] = bf16_hi_of(gq[1].x); gf[2] = bf16_lo_of(gq[1].y); gf[3] = bf16_hi_of(gq[1].y);
-            gg[0] = bf16_lo_of(gq[2].x); gg[1] = bf16_hi_of(gq[2].x); gg[2] = bf16_lo_of(gq[2].y); gg[3] = bf16_hi_of(gq[2].y);
-            go[0] = bf16_lo_of(gq[3].x); go[1] = bf16_hi_of(gq[3].x); go[2] = bf16_lo_of(gq[3].y); go[3] = bf16_hi_of(gq[3].y);
+            // the stash holds the activations as fp16 (pack8_stash); dG goes back in place as bf16
+            { const float2 a = half2_to_float2(gq[0].x), b = half2_to_float2(gq[0].y); gi[0] = a.x; gi[1] = a.y; gi[2] = b.x; gi[3] = b.y; }
+            { const float2 a = half2_to_float2(gq[1].x), b = half2_to_float2(gq[1].y); gf[0] = a.x; gf[1] = a.y; gf[2] = b.x; gf[3] = b.y; }
+            { const float2 a = half2_to_float2(gq[2].x), b = half2_to_float2(gq[2].y); gg[0] = a.x; gg[1] = a.y; gg[2] = b.x; gg[3] = b.y; }
+            { const float2 a = half2_to_float2(gq[3].x), b = half2_to_float2(gq[3].y); go[0] = a.x; go[1] = a.y; go[2] = b.x; go[3] = b.y; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float tc = tanh_approx(ct[i]);
@@ -595,6 +597,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     for (int r64 = 0; r64 < 64; ++r64) sum += bsc[r64 * 128 + threadIdx.x];
     const int pc = ns * 128 + threadIdx.x;                           // packed column
     const int r = ((pc & 31) >> 3) * H + (pc >> 5) * 8 + (pc & 7);   // reference row (gate-major i|f|g|o)
+    sum *= __ldg(p.inv_scale);
     ly.gbias_ih[r] = sum;
     ly.gbias_hh[r] = sum;
   }
@@ -606,11 +609,10 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
 template <int H>
 static int launch_wbptt(WbParams& p, cudaStream_t s) {
   auto kern = wbptt_kernel<H>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;        // one bit per device
+  if (first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWbSmem);
     if (e != cudaSuccess) { set_error("wbptt: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(4 * (2 * p.L - 1) * (H / 128));

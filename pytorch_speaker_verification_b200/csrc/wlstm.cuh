@@ -484,10 +484,10 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         }
         if (p.ablate & 2) continue;
         if (p.training) {
-          // gate stash [row][packed col] bf16: two boxes of 64 columns, 128B-swizzled rows
+          // gate stash [row][packed col] fp16 (see pack8_stash): two boxes of 64 columns, 128B-swizzled rows
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const uint32_t pk = pack_bf16x2(a[i], a[i + 1]);
+            const uint32_t pk = pack_f16x2(a[i], a[i + 1]);
             sts_u16((gbase0 ^ ((i & 7) << 4)) + ps * 4096 + i * 128, (uint16_t)(pk & 0xffffu));
             sts_u16((gbase0 ^ (((i + 1) & 7) << 4)) + ps * 4096 + (i + 1) * 128, (uint16_t)(pk >> 16));
           }
@@ -618,11 +618,10 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
 template <int H>
 static int launch_wlstm_fwd(WlstmParams& p, cudaStream_t s) {
   auto kern = wlstm_fwd_kernel<H>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;        // one bit per device
+  if (first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWlSmem);
     if (e != cudaSuccess) { set_error("wlstm: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
-    configured = true;
   }
   void* args[] = {&p};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3(2 * p.L * (H / 32)), dim3(kWlThreads), args, kWlSmem, s);

@@ -23,8 +23,7 @@ def speaker_shard(n_speakers, rank, world):
 
 
 def _fused_loss_and_grads(E, w, b):
-    r = ops._ge2e_call(E, None, w, b, None, None, False, True, True, True)
-    return r["loss"], r["dE"], r["dw"], r["db"]
+    return torch.ops.svb200.ge2e_loss(E, w, b, 1, True)
 
 
 class _GlobalGE2EFn(torch.autograd.Function):
@@ -43,9 +42,7 @@ class _GlobalGE2EFn(torch.autograd.Function):
     def backward(ctx, g):
         dE, dw, db = ctx.saved_tensors
         if dE.device.type == "cuda":
-            dE, dw, db = dE.clone(), dw.clone(), db.clone()
-            ops.check(ops._lib.lib().svb_scale3(ops.ptr(dE), ops._sz(dE.numel()), ops.ptr(dw), ops._sz(1), ops.ptr(db),
-                                                ops._sz(1), ops.ptr(g.contiguous()), ops.stream_ptr()), "svb_scale3")
+            dE, dw, db = torch.ops.svb200.scale3(dE, dw, db, g)
         else:                       # host-logic tests (gloo, injected compute)
             dE, dw, db = dE * g, dw * g, db * g
         return dE, dw, db, None, None
@@ -91,9 +88,15 @@ class OverlappedGradReducer:
         reducer = OverlappedGradReducer()
         with reducer:
             loss.backward()
-        reducer.finish()            # the current stream waits for the four all-reduces
 
-    Every rank issues the same buckets in the same order (the order is fixed by the library)."""
+    Every rank issues the same buckets in the same order (the order is fixed by the library).
+
+    The buckets are slices of the flat buffer the backward op returns its gradients in.  Before the op hands that
+    buffer to autograd, ``finish()`` makes the compute stream wait for the all-reduces (called by the op itself, see
+    ops.set_grad_bucket_hook), so whatever autograd then does with the gradients -- adopt the views as ``p.grad``
+    (``zero_grad(set_to_none=True)``), add them to an existing ``p.grad`` (``set_to_none=False``, gradient
+    accumulation over micro-batches), run parameter hooks -- happens on REDUCED values.  The transfers still overlap
+    every kernel of the backward that follows their bucket; only the last bucket (layer 0) has nothing after it."""
 
     def __init__(self, group=None, all_reduce=None):
         self.group = group
@@ -107,15 +110,17 @@ class OverlappedGradReducer:
         self.works.append(self._all_reduce(bucket))
 
     def __enter__(self):
-        ops.set_grad_bucket_hook(self._hook)
+        ops.set_grad_bucket_hook(self._hook, self.finish)
         return self
 
     def __exit__(self, *exc):
         ops.set_grad_bucket_hook(None)
+        self.finish()
         return False
 
     def finish(self):
-        for w in self.works:
+        """The current stream waits for every all-reduce started so far (idempotent)."""
+        works, self.works = self.works, []
+        for w in works:
             if w is not None:
                 w.wait()
-        self.works = []

@@ -38,8 +38,9 @@ def get_windows(S):
     """S (nmels, T) log-mel -> (W, 24, nmels) float32 tensor on S's device (CPU input is staged through the GPU)."""
     S = torch.as_tensor(S)
     out_device = S.device
-    with torch.cuda.device(ops._dev()):
-        Sg = ops._stage(S, torch.float32)
+    dev = ops._target_device(S)
+    with torch.cuda.device(dev):
+        Sg = ops._stage(S, torch.float32, dev)
         starts = torch.from_numpy(window_starts(int(S.shape[1]))).to(Sg.device)
         out = ops.dvector_windows(Sg, starts, WIN)
     return out if out_device.type == "cuda" else out.to(out_device)
@@ -48,8 +49,9 @@ def get_windows(S):
 def align_embeddings(embeddings):
     """(W, D) window embeddings -> (P, D) float64 numpy array of partition means (dvector_create.py:55-73)."""
     emb = torch.as_tensor(embeddings)
-    with torch.cuda.device(ops._dev()):
-        eg = ops._stage(emb.detach(), torch.float32)
+    dev = ops._target_device(emb)
+    with torch.cuda.device(dev):
+        eg = ops._stage(emb.detach(), torch.float32, dev)
         offs = torch.from_numpy(partition_offsets(int(eg.shape[0]))).to(eg.device)
         out = ops.segment_mean(eg, offs)
     return out.cpu().numpy()
@@ -120,7 +122,7 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
     asynchronous H2D copy, one window-gather launch, the LSTM on <= max_windows windows at a time, one segment-mean
     launch and an asynchronous D2H copy into pinned memory.  Nothing synchronises until the last chunk is queued, so
     the host-side staging and index math of chunk i+1 overlap the GPU work of chunk i."""
-    dev = ops._dev()
+    dev = ops._target_device(*embedder_net.parameters())        # the module's device, else the current one
     D = embedder_net.projection.out_features
     n = len(specs)
     if n == 0:

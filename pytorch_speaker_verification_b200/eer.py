@@ -24,8 +24,9 @@ def eer_sweep(sim_matrix, thresholds=None):
     double threshold, or the integers 0 when no threshold ever satisfied ``diff > |FAR-FRR|``."""
     thresholds = THRESHOLDS if thresholds is None else list(thresholds)
     out_device = sim_matrix.device
-    with torch.cuda.device(ops._dev()):
-        sim = ops._stage(sim_matrix.detach(), torch.float32)
+    dev = ops._target_device(sim_matrix)
+    with torch.cuda.device(dev):
+        sim = ops._stage(sim_matrix.detach(), torch.float32, dev)
         thr = _thresholds_f32(sim.device, thresholds)
         if sim.shape[0] == sim.shape[2] and sim.shape[0] >= 2 and len(thresholds) < 64 and sim.shape[1] * sim.shape[2] < (1 << 23):
             out_d, ca, cd = ops.eer_sweep_fused(sim, thr)

@@ -6,14 +6,12 @@ The tables (periodic Hann window padded to n_fft, DFT twiddles, Slaney mel filte
 float64 and handed to svb_logmel; the arithmetic runs in libsvb200.so (csrc/frontend.cu), no CPU fallback.
 Parity is unpinned: librosa is not available where this was built, see oracle/frontend.py.
 """
-import ctypes
 import math
 
 import numpy as np
 import torch
 
-from . import _lib, ops
-from ._lib import check, ptr, stream_ptr
+from . import ops
 
 N_FFT = 512
 _tables = {}
@@ -58,15 +56,13 @@ def log_mel_spectrogram(y, sr=16000, win_length=400, hop=160, n_mels=40):
     data_preprocess.py:45 / dvector_create.py:47 (n_fft = 512)."""
     if win_length > N_FFT:
         raise ValueError("win_length must be <= n_fft = 512")
-    dev = ops._dev()
+    y = torch.as_tensor(y)
+    dev = ops._target_device(y)
     with torch.cuda.device(dev):
-        yg = ops._stage(torch.as_tensor(y), torch.float32).reshape(-1)
+        yg = ops._stage(y, torch.float32, dev).reshape(-1)
         n = int(yg.numel())
         if n <= N_FFT // 2:
             raise ValueError("reflect padding needs more than n_fft/2 samples (librosa raises here too)")
         win, w0, w1, tw, melw = _get_tables(dev, sr, win_length, n_mels)
-        n_frames = 1 + n // hop
-        out = torch.empty(n_mels, n_frames, dtype=torch.float32, device=dev)
-        check(_lib.lib().svb_logmel(ptr(yg), ctypes.c_int64(n), int(hop), ptr(win), w0, w1, ptr(tw), ptr(melw), n_mels,
-                                    ptr(out), n_frames, stream_ptr()), "svb_logmel")
+        out = torch.ops.svb200.logmel(yg, win, tw, melw, int(hop), w0, w1)
     return out

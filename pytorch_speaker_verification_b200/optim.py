@@ -14,7 +14,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import check
+from . import ops  # noqa: F401  (registers torch.ops.svb200)
 
 
 class FusedClipSGD:
@@ -46,7 +47,7 @@ class FusedClipSGD:
     @torch.no_grad()
     def step(self):
         """Returns the pre-clip total norms, one per group (device tensor; what clip_grad_norm_ returns)."""
-        params, grads, numel, group, max_norm = [], [], [], [], []
+        params, grads, group, max_norm = [], [], [], []
         dev = None
         for gi, g in enumerate(self.param_groups):
             mn = g["max_norm"]
@@ -64,23 +65,16 @@ class FusedClipSGD:
                     raise _lib.SvbError("FusedClipSGD: all parameters must live on one device")
                 params.append(p)
                 grads.append(gr)
-                numel.append(p.numel())
                 group.append(gi)
         if not params:
             return None
-        n, ng = len(params), len(self.param_groups)
         with torch.cuda.device(dev):
             if self._ws is None or self._ws.device != dev:
                 nb = ctypes.c_size_t(0)
                 check(_lib.lib().svb_clip_sgd_workspace_bytes(ctypes.byref(nb)), "svb_clip_sgd_workspace_bytes")
                 self._ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-                self._norms = torch.empty(4, dtype=torch.float32, device=dev)
-            check(_lib.lib().svb_clip_sgd((ctypes.c_void_p * n)(*[p.data_ptr() for p in params]),
-                                          (ctypes.c_void_p * n)(*[g.data_ptr() for g in grads]),
-                                          (ctypes.c_int64 * n)(*numel), (ctypes.c_int32 * n)(*group), n,
-                                          (ctypes.c_float * ng)(*max_norm), ng, ctypes.c_float(self.lr),
-                                          int(self.write_clipped_grads), ptr(self._norms), ptr(self._ws),
-                                          ctypes.c_size_t(self._ws.numel()), stream_ptr()), "svb_clip_sgd")
-        for p in params:                      # the packed fp16/bf16 weight shadows key on Parameter._version
-            torch.autograd.graph.increment_version(p)
-        return self._norms[:ng]
+            # the op declares params / grads as mutated, so autograd's version counters advance (the packed
+            # fp16/bf16 weight shadows key on Parameter._version)
+            self._norms = torch.ops.svb200.clip_sgd(params, grads, group, max_norm, self.lr, self.write_clipped_grads,
+                                                    self._ws)
+        return self._norms

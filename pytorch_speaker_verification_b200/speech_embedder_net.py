@@ -40,8 +40,14 @@ class SpeechEmbedder(nn.Module):
                 ps.append(getattr(self.LSTM_stack, f"{k}_l{l}"))
         return ps + [self.projection.weight, self.projection.bias]
 
+    def repack(self):
+        """Rebuild the fp16/bf16 weight shadows on the next call.  Only needed after in-place surgery that bypasses
+        autograd's version counter (``p.data.copy_()``, ``p.data.add_()``); optimizers, ``load_state_dict`` and
+        ``.to()`` / ``.cpu()`` are detected automatically."""
+        self._cache.invalidate()
+
     def forward(self, x):
-        return ops.EmbedderFn.apply(x, self._cache, (*self._dims, int(self.recurrent_terms)), *self._ordered_params())
+        return ops.embedder_forward(x, self._cache, (*self._dims, int(self.recurrent_terms)), self._ordered_params())
 
 
 class GE2ELoss(nn.Module):
@@ -56,4 +62,4 @@ class GE2ELoss(nn.Module):
 
     def forward(self, embeddings):
         # speech_embedder_net.py:44 `torch.clamp(self.w, 1e-6)` discards its result: w is NOT clamped.
-        return ops.GE2ELossFn.apply(embeddings, self.w, self.b, self.fused)
+        return ops.ge2e_loss(embeddings, self.w, self.b, int(self.fused))
