@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the GE2E training hot path (BASELINE.json metric: train utts/sec, LSTM+GE2E fwd+bwd, N=64 M=10).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda]
 
 One JSON line on stdout (rank 0).  Workload = BASELINE.json configs[1]: 64 speakers x 10 utterances x 160 frames x
 40 mel per GPU, synthetic log-mel, reference-initialised weights.  Under torchrun (N > 1) every rank owns 64
@@ -13,6 +13,9 @@ gradients are all-reduced (SUM).
           backward, the two clip_grad_norm_ and the SGD step of train_speech_embedder.py:54-65, D2H of the loss
   --impl reference : the reference's CPU path (oracle port calling the same torch CPU library entry points the
           reference calls), all host threads, on a bounded sample of the same workload.
+  --impl reference-cuda : the UNMODIFIED reference modules (baseline/_ref) on the same GPU through stock torch CUDA
+          (cuDNN nn.LSTM, eager GE2E, clip_grad_norm_ x2, SGD): the kernel-vs-kernel bar.  The default run also
+          carries these numbers as `gpu_baseline` (N = 1) next to `cpu_baseline`.
 """
 import argparse
 import ctypes
@@ -144,15 +147,48 @@ class ClockSampler:
 
 
 def launches_per_step(world):
-    """Our kernels per `value` step (fwd + GE2E + bwd), as listed by ncu in profiles/r1c_launches_step_summary.txt."""
+    """Fallback when CUPTI is unavailable: our kernels per `value` step as listed by ncu (profiles/*launches_step*)."""
     fwd = 1 + 1 + 2                                    # prep_x, persistent wavefront LSTM kernel, projection GEMM + finish
     loss = 1                                           # GE2E (per-speaker kernel; general kernel for the global batch)
-    bwd = (1 + 5 + 1                                   # scale3, projection bwd (norm, 2 GEMMs, add2, colsum), persistent BPTT
+    bwd = (1 + 5 + 1 + 1                               # scale3, projection bwd (norm, 2 GEMMs, add2, colsum), gradient scale, persistent BPTT
            + NLAYER                                    # frame gates of the late weight-gradient slices
            + 2 * (2 * NLAYER - 1)                      # early + late slices of the 5 wide weight-gradient products
            + 2                                         # layer-0 dW_ih (N = 40) + its slice sum
            + (2 * NLAYER - 1))                         # sum of the three partials per wide product
     return fwd + loss + bwd
+
+
+def count_launches(L, fn, torch):
+    """-> (our kernel launches, other launches, {kernel: count}) of one call of fn, seen through CUPTI's callback API
+    (svb_launch_count_*: a launch is ours when its host stub lives in libsvb200.so), or None without CUPTI."""
+    if L.svb_launch_count_begin() != 0:
+        return None
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        ours, other = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        names = ctypes.create_string_buffer(1 << 16)
+        L.svb_launch_count_end(ctypes.byref(ours), ctypes.byref(other), names, ctypes.c_size_t(len(names)))
+    per = {}
+    for item in names.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.rsplit("=", 1)
+            per[k] = int(v)
+    return ours.value, other.value, per
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed summary
+    of this round's `ncu --set full` capture (profiles/r2_traffic.json, written by scripts/summarize_ncu.py); None
+    when that capture does not exist -- never a number carried over from another build."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(kernel_key)
+        return None if e is None else int(e["dram_bytes_read"] + e["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 def cpu_reference_rate(steps, warmup, budget_s=150.0):
@@ -187,7 +223,7 @@ def cpu_reference_rate(steps, warmup, budget_s=150.0):
     return n * M_UTT / dt, sample, cores, dt
 
 
-def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
+def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world, n_extract=12500):
     """The other rows of SURVEY section 8: d-vector extraction (configs[3] shape, scaled down to a bounded shard per
     GPU), the EER sweep at configs[4] size and the fused GE2E kernel alone; device time via CUDA events."""
     import ctypes
@@ -209,9 +245,10 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    # ---- d-vector extraction: 2000 utterances per GPU, T_u ~ U[100, 500] frames, from host log-mel arrays
+    # ---- d-vector extraction, BASELINE configs[3]: 100k utterances over 8 GPUs = 12,500 per GPU (every rank takes its
+    # own 12,500: weak scaling), T_u ~ U[100, 500] frames, from host log-mel arrays
     r = np.random.RandomState(4321 + rank)
-    Ts = r.randint(100, 501, size=2000)
+    Ts = r.randint(100, 501, size=n_extract)
     specs = [np.log10(I.power_spec(int(T), seed=int(T) + 7 * i) + 1e-6).astype(np.float32) for i, T in enumerate(Ts[:64])]
     specs = [specs[i % 64][:, :int(T)] if specs[i % 64].shape[1] >= T else np.tile(specs[i % 64], (1, 8))[:, :int(T)]
              for i, T in enumerate(Ts)]
@@ -232,8 +269,12 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world):
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out["extraction"] = {"utterances_per_gpu": len(specs), "windows_per_gpu": nwin, "dvectors_per_gpu": ndv,
-                         "seconds": t.item(), "windows_per_s": world * nwin / t.item(),
+    out["extraction"] = {"utterances_per_gpu": len(specs), "utterances_total": world * len(specs),
+                         "windows_per_gpu": nwin, "dvectors_per_gpu": ndv,
+                         "seconds": t.item(), "seconds_all_runs": [round(v, 4) for v in dts],
+                         "windows_per_s": world * nwin / t.item(),
+                         "frac_of_tensor_roofline": (nwin / t.item()) * 572522496.0 / 1e12 /
+                         peaks()[0].get("bf16_tflops_sustained", 1400.0),
                          "dvectors_per_s": world * ndv / t.item(), "utterances_per_s": world * len(specs) / t.item(),
                          "path": "host log-mel -> H2D -> window gather -> LSTM fwd (T=24) -> partition mean -> D2H"}
     # device-resident part only: LSTM forward of 32768 windows x 24 frames already in HBM (the tensor-bound core)
@@ -352,12 +393,74 @@ def run_reference(args, rank):
     emit(line)
 
 
+def gpu_baseline_block(torch, I, dev, steps, warmup, flush=None, full=True):
+    """The reference on the same GPU through stock torch CUDA (bench_reference_arms.TorchCudaReference): C2 train step
+    with cuDNN nn.LSTM in fp32 (torch's default: TF32 allowed for cuDNN) and under bf16 autocast, plus -- `full` -- the
+    secondary rows (GE2E alone at C2 / C3, get_cossim + threshold loop at C5, a T = 24 extraction batch)."""
+    from bench_reference_arms import TorchCudaReference
+    ref = TorchCudaReference(torch, dev)
+    B = N_SPK * M_UTT
+    x_host = torch.tensor(I.logmel(B, T_FR, seed=1234)).pin_memory()
+    out = {"kind": ref.kind, "library": f"torch {torch.__version__}, cuDNN {torch.backends.cudnn.version()}",
+           "source": "baseline/_ref (unmodified reference modules)" if ref.kind == "reference" else
+                     "oracle port of the reference's library calls (baseline/_ref not staged)",
+           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+           "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)}
+    for tag, ac in (("fp32", False), ("bf16_autocast", True)):
+        ms_full, ms_value = ref.train_step(x_host, N_SPK, M_UTT, steps, warmup, autocast_bf16=ac, flush=flush)
+        out[f"train_step_{tag}"] = {"ms_per_step_fwd_loss_bwd": ms_value, "utts_per_s": B / (ms_value * 1e-3),
+                                    "ms_per_step_e2e": ms_full, "utts_per_s_e2e": B / (ms_full * 1e-3)}
+        torch.cuda.empty_cache()
+    if full:
+        out["ge2e_fwd_bwd_N64_us"] = ref.ge2e_only(I.ge2e_embeddings(64, 10, 256, "unit")) * 1e3
+        out["ge2e_fwd_bwd_N512_us"] = ref.ge2e_only(I.ge2e_embeddings(512, 10, 256, "unit"), steps=5, warmup=2) * 1e3
+        torch.cuda.empty_cache()
+        enr, ver = I.eer_embeddings(1024, 6, 0.06, 0.5, 4242)
+        e = ref.eer(enr, ver)
+        if e is not None:
+            out["eer_N1024"] = {"cossim_from_embeddings_us": e[0] * 1e3, "threshold_loop_us": e[1] * 1e3, "eer": e[2],
+                                "loop": "train_speech_embedder.py:132-149 executed from baseline/_ref on CUDA tensors"}
+        torch.cuda.empty_cache()
+        xw = torch.tensor(I.logmel(4096, 24, seed=99)).to(dev).repeat(8, 1, 1)
+        ms = ref.forward_windows(xw)
+        out["lstm_forward_windows_per_s_device_resident"] = xw.shape[0] / (ms * 1e-3)
+        del xw
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_cuda(args, rank, local_rank):
+    """--impl reference-cuda: one JSON line in the main line's format, measured on the reference's stock-torch path."""
+    if rank != 0:
+        return
+    import torch
+    import _inputs as I
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    blk = gpu_baseline_block(torch, I, dev, steps, warm, flush=flush, full=True)
+    B = N_SPK * M_UTT
+    best = blk["train_step_fp32"]
+    line = {"impl": "reference-cuda", "metric": METRIC, "value": best["utts_per_s"], "unit": "utts/s", "n_gpus": 1,
+            "steps": steps, "warmup": warm, "ms_per_step": best["ms_per_step_fwd_loss_bwd"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN, TF32 allowed)", "data": "synthetic",
+            "config": {"workload": "GE2E train step N=64 x M=10, 160 frames x 40 mel (BASELINE configs[1])",
+                       "l2": "192 MiB buffer written between timed iterations (untimed)"},
+            "e2e": {"value": best["utts_per_s_e2e"], "unit": "utts/s", "ms_per_step": best["ms_per_step_e2e"],
+                    "h2d_bytes_per_step": B * T_FR * NMELS * 4, "d2h_bytes_per_step": 4},
+            "gpu_baseline": blk}
+    emit(line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--extract-utts", type=int, default=12500, help="utterances per GPU of the extraction row (configs[3]: 100k over 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--recurrent-terms", type=int, default=1)
     args = ap.parse_args()
@@ -372,6 +475,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "reference-cuda":
+        run_reference_cuda(args, rank, local_rank)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -500,7 +606,8 @@ def main():
     phases = phase_profile(value_step)          # every rank: the step contains collectives
     barrier()
     loss_val = float(loss_host)
-    extra = secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world)
+    launch_count = count_launches(L, value_step, torch)      # one extra, untimed step seen through CUPTI
+    extra = secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world, args.extract_utts)
     extra["e2e_with_prefetch_and_fused_clip_sgd"] = {
         "value": B * world / (ms_e2e_fused * 1e-3), "unit": "utts/s", "ms_per_step": ms_e2e_fused,
         "step": "svb.prefetch (H2D of the next pinned batch on a copy stream) + zero_grad + fwd + GE2E + bwd + "
@@ -539,7 +646,8 @@ def main():
         line = {
             "metric": METRIC, "value": utts / (ms_value * 1e-3), "unit": "utts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate",
+            "data": "synthetic",
             "config": {"workload": "GE2E train step, 64 speakers x 10 utts x 160 frames x 40 mel per GPU "
                                    "(BASELINE configs[1]; global batch = 64 x n_gpus speakers, configs[2] at 8)",
                        "model": "3-layer LSTM 40->768, Linear 768->256, L2 norm; GE2E w=10 b=-5; reference init seed 0",
@@ -550,16 +658,18 @@ def main():
                        "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
             "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utts/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches_per_step(world) * args.steps,
+            "gpu_launches": (launch_count[0] if launch_count else launches_per_step(world)) * args.steps,
+            "gpu_launches_detail": ({"per_step": launch_count[0], "other_libraries_per_step": launch_count[1],
+                                     "kernels": launch_count[2],
+                                     "source": "CUPTI callback count of one extra untimed step (svb_launch_count_*)"}
+                                    if launch_count else {"per_step": launches_per_step(world),
+                                                          "source": "formula (CUPTI unavailable)"}),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r1_ncu_full_summary.txt); the frame kernels' writes stay in the 126 MB L2
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r1b_ncu_full_persistent_summary.txt)
-                         "traffic": {"recurrent_bwd": 2940671000 + 2289802000,
-                                     "recurrent_fwd": 1238112000 + 7455558000}.get(dom) if args.recurrent_terms == 1 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from this round's ncu --set full
+                         # capture (profiles/r2_traffic.json), else null
+                         "traffic": measured_traffic(dom) if args.recurrent_terms == 1 else None,
                          "peak_source": f"{pk_src} (sustained bf16)",
                          "avg_launch_us": avg_ms * 1e3, "launches_per_step": launches,
                          # whole step against the 3x-forward convention of BASELINE.md (11,443,765,248 FLOP/utt)
@@ -571,9 +681,65 @@ def main():
             "secondary": extra,
             "loss": loss_val,
         }
+        accounted = sum(phases.values())
+        line["phases_ms"]["unattributed"] = ms_value - accounted
+        line["phases_note"] = ("phases_ms are CUDA-event brackets inside svb_embedder_forward/backward; `unattributed` = "
+                               "ms_per_step - their sum: the GE2E launch, autograd / custom-op dispatch gaps between "
+                               "the library calls, and (N > 1) the all-gather and the gradient all-reduce")
+        if world == 1 and not args.no_gpu_baseline:
+            del flush
+            torch.cuda.empty_cache()
+            try:
+                line["gpu_baseline"] = gpu_baseline_block(torch, I, dev, max(3, min(args.steps, 10)), 3)
+            except Exception as exc:          # the reference arm must never take the main line down
+                line["gpu_baseline"] = {"unavailable": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             rate, sample, cores, _ = cpu_reference_rate(2, 1, budget_s=40.0)
             line["cpu_baseline"] = {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample}
+            try:
+                from bench_reference_arms import cpu_secondary
+                line["cpu_baseline"]["secondary"] = cpu_secondary(torch, I)
+            except Exception as exc:
+                line["cpu_baseline"]["secondary"] = {"unavailable": repr(exc)}
+        gb, cb = line.get("gpu_baseline") or {}, (line.get("cpu_baseline") or {}).get("secondary") or {}
+        if world == 1 and ("train_step_fp32" in gb or cb):
+            sec = line["secondary"]
+
+            def g(d, *ks):
+                for k in ks:
+                    d = d.get(k) if isinstance(d, dict) else None
+                return d
+
+            rows = {
+                "train_step_utts_per_s": {"ours": line["value"], "ours_e2e": line["e2e"]["value"],
+                                          "torch_cuda_fp32": g(gb, "train_step_fp32", "utts_per_s"),
+                                          "torch_cuda_fp32_e2e": g(gb, "train_step_fp32", "utts_per_s_e2e"),
+                                          "torch_cuda_bf16_autocast": g(gb, "train_step_bf16_autocast", "utts_per_s"),
+                                          "cpu": g(line, "cpu_baseline", "value")},
+                "ge2e_fwd_bwd_N64_us": {"ours": g(sec, "ge2e_fwd_bwd_N64", "us"), "torch_cuda": gb.get("ge2e_fwd_bwd_N64_us"),
+                                        "cpu": cb.get("ge2e_fwd_bwd_N64_ms") and cb["ge2e_fwd_bwd_N64_ms"] * 1e3},
+                "ge2e_fwd_bwd_N512_us": {"ours": g(sec, "ge2e_fwd_bwd_N512", "us"), "torch_cuda": gb.get("ge2e_fwd_bwd_N512_us")},
+                "eer_N1024_cossim_us": {"ours": g(sec, "eer", "cossim_from_embeddings_us"),
+                                        "torch_cuda": g(gb, "eer_N1024", "cossim_from_embeddings_us"),
+                                        "cpu": g(cb, "eer_N1024", "cossim_ms") and cb["eer_N1024"]["cossim_ms"] * 1e3},
+                "eer_N1024_threshold_sweep_us": {"ours": g(sec, "eer", "sweep_us"),
+                                                 "torch_cuda": g(gb, "eer_N1024", "threshold_loop_us"),
+                                                 "cpu": g(cb, "eer_N1024", "threshold_loop_ms") and cb["eer_N1024"]["threshold_loop_ms"] * 1e3},
+                "extraction_windows_per_s": {"ours_e2e_from_host": g(sec, "extraction", "windows_per_s"),
+                                             "ours_device_resident": g(sec, "extraction", "lstm_forward_windows_per_s_device_resident"),
+                                             "torch_cuda_device_resident": gb.get("lstm_forward_windows_per_s_device_resident"),
+                                             "cpu_per_file": g(cb, "extraction", "windows_per_s")},
+            }
+            lower_is_better = {"ge2e_fwd_bwd_N64_us", "ge2e_fwd_bwd_N512_us", "eer_N1024_cossim_us", "eer_N1024_threshold_sweep_us"}
+            lost = []
+            for name, r in rows.items():
+                ours = [v for k, v in r.items() if k.startswith("ours") and v]
+                theirs = [v for k, v in r.items() if k.startswith("torch_cuda") and v]
+                if ours and theirs:
+                    if (name in lower_is_better and min(theirs) < min(ours)) or (name not in lower_is_better and max(theirs) > max(ours)):
+                        lost.append(name)
+            line["side_by_side"] = {"rows": rows, "rows_where_stock_torch_cuda_wins": lost,
+                                    "cpu_cores": (line.get("cpu_baseline") or {}).get("cores")}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

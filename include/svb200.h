@@ -98,6 +98,13 @@ int svb_set_trace_bwd(unsigned long long* device_buffer);
 int svb_profile_enable(int on);
 int svb_profile_read(float* ms_per_phase, int nphases);
 
+/* Launch counter (measurement only; bench.py's gpu_launches): between begin and end, every kernel launch of the process
+ * is seen through CUPTI's callback API; `ours` = launches whose host stub lives in this library, `other` = everyone
+ * else's (torch, NCCL); names = "mangled_kernel_name=count;..." of ours.  SVB_ERR_UNSUPPORTED when libcupti cannot be
+ * opened or another CUPTI client (a profiler) is attached. */
+int svb_launch_count_begin(void);
+int svb_launch_count_end(long long* ours, long long* other, char* names, size_t names_bytes);
+
 /* ---- GE2E loss (speech_embedder_net.py:35-49, utils.py:27-132) ---------------------------------------------------- */
 
 int svb_ge2e_workspace_bytes(int N, int M, int D, int Nc, size_t* bytes);

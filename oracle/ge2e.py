@@ -21,9 +21,67 @@ COS_BIAS = 1e-6    # utils.py:114
 LOG_BIAS = 1e-6    # utils.py:129
 
 
+def _cascade(rows):
+    """Cascade summation of a list of equally shaped float32 arrays (ATen SumKernel.cpp multi_row_sum): sequential
+    into a level-0 accumulator that is flushed into level 1 every 16 rows, level 1 into level 2 every 256, level 2
+    into level 3 every 4096; the remaining rows go to level 0 and the levels are added in order."""
+    M = len(rows)
+    z = np.zeros_like(rows[0]) if M else None
+    acc = [z.copy() for _ in range(4)]
+    i = 0
+    while i + 16 <= M:
+        for _ in range(16):
+            acc[0] = acc[0] + rows[i]
+            i += 1
+        for j in range(1, 4):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = z.copy()
+            if (i & (15 << (4 * j))) != 0:
+                break
+    while i < M:
+        acc[0] = acc[0] + rows[i]
+        i += 1
+    for j in range(1, 4):
+        acc[0] = acc[0] + acc[j]
+    return acc[0]
+
+
+def sum_utterances_torch_order(E, vec_chunk=32):
+    """``E.sum(dim=1)`` of a contiguous (N, M, D) float32 tensor in the order torch's CPU kernel adds the rows (ATen
+    SumKernel.cpp, vectorized_outer_sum with 256-bit vectors -- the kernel torch selects in this image):
+      * columns [0, 32 * (D // 32)): cascade summation over the rows (plain sequential for M < 16);
+      * the remaining columns: ``row_sum`` -- four interleaved partial sums over rows i = k mod 4 (each a cascade over
+        M // 4 rows), the M % 4 tail rows added to partial 0, then p0 + p1 + p2 + p3.
+    Pinned against the reference by tests/golden/centroids.npz."""
+    N, M, D = E.shape
+    out = np.empty((N, D), dtype=E.dtype)
+    dv = vec_chunk * (D // vec_chunk)
+    if dv:
+        out[:, :dv] = _cascade([E[:, i, :dv] for i in range(M)])
+    if dv < D:
+        q = M // 4
+        part = [_cascade([E[:, 4 * i + k, dv:] for i in range(q)]) if q else np.zeros((N, D - dv), dtype=E.dtype)
+                for k in range(4)]
+        for i in range(4 * q, M):
+            part[0] = part[0] + E[:, i, dv:]
+        out[:, dv:] = ((part[0] + part[1]) + part[2]) + part[3]
+    return out
+
+
 def get_centroids(E):
     """utils.py:27-29 -- mean over the utterance axis."""
     return E.mean(axis=1)
+
+
+def get_centroids_bitwise(E):
+    """utils.py:27-29 with torch's float32 operation order: cascade sum, then one division by M."""
+    return (sum_utterances_torch_order(E) / E.dtype.type(E.shape[1])).astype(E.dtype)
+
+
+def get_utterance_centroids_bitwise(E):
+    """utils.py:40-58 with torch's float32 operation order: (cascade sum - E) / (M - 1)."""
+    s = sum_utterances_torch_order(E)[:, None, :]
+    return ((s - E).astype(E.dtype) / E.dtype.type(E.shape[1] - 1)).astype(E.dtype)
 
 
 def get_utterance_centroids(E):

@@ -1014,11 +1014,14 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
 }
 
 // Sum over the utterance axis in the order torch's CPU sum kernel uses for this layout (reduction over a strided
-// dimension with a contiguous inner dimension of at least one SIMD vector: ATen SumKernel.cpp, cascade summation):
-// rows are added sequentially into a level-0 accumulator that is flushed into level 1 every 16 rows, level 1 into
-// level 2 every 256, level 2 into level 3 every 4096; remaining rows go to level 0 and the levels are added in order.
-// For M < 16 (every batch shape the reference uses) this is the plain sequential sum.  Bit-exact against the
-// reference's `embeddings.sum(dim=1)` / `.mean(dim=1)` for D >= 16 (tests/golden/centroids.npz).
+// dimension with a contiguous inner dimension: ATen SumKernel.cpp, vectorized_outer_sum with 256-bit vectors, the
+// kernel torch selects in the build image):
+//   * columns [0, 32 (D / 32)): cascade summation -- rows are added sequentially into a level-0 accumulator that is
+//     flushed into level 1 every 16 rows, level 1 into level 2 every 256, level 2 into level 3 every 4096; remaining
+//     rows go to level 0 and the levels are added in order (plain sequential for M < 16, the reference's shapes);
+//   * the remaining columns: four interleaved partial sums over rows i = k mod 4 (each a cascade over M / 4 rows), the
+//     M % 4 tail rows added to partial 0, then p0 + p1 + p2 + p3.
+// Bit-exact against the reference's `embeddings.sum(dim=1)` / `.mean(dim=1)` (tests/golden/centroids.npz).
 __device__ __forceinline__ float cascade_sum_rows(const float* __restrict__ x, int M, size_t stride) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int i = 0;
@@ -1035,12 +1038,21 @@ __device__ __forceinline__ float cascade_sum_rows(const float* __restrict__ x, i
   a0 = __fadd_rn(a0, a2);
   return __fadd_rn(a0, a3);
 }
+__device__ __forceinline__ float torch_order_sum_rows(const float* __restrict__ x, int M, int D, int d) {
+  if (d < 32 * (D / 32)) return cascade_sum_rows(x, M, D);
+  const int q = M / 4;
+  float p[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p[k] = cascade_sum_rows(x + (size_t)k * D, q, (size_t)4 * D);
+  for (int i = 4 * q; i < M; ++i) p[0] = __fadd_rn(p[0], x[(size_t)i * D]);
+  return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+}
 // get_centroids (utils.py:27-29): C[j, d] = mean_m E[j, m, d]; backward: dE[j, m, d] = dC[j, d] / M.
 __global__ void centroid_kernel(const float* __restrict__ E, float* __restrict__ C, int N, int M, int D) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * D) return;
   const int j = i / D, d = i % D;
-  C[i] = __fdiv_rn(cascade_sum_rows(E + (size_t)j * M * D + d, M, D), (float)M);
+  C[i] = __fdiv_rn(torch_order_sum_rows(E + (size_t)j * M * D + d, M, D, d), (float)M);
 }
 // get_utterance_centroids (utils.py:40-58): U[j, i, :] = (sum_m E[j, m, :] - E[j, i, :]) / (M - 1), the same three
 // float32 operations (sum over dim 1, subtract, divide) in the same order.  The operator is linear and symmetric, so
@@ -1050,7 +1062,7 @@ __global__ void utterance_centroid_kernel(const float* __restrict__ E, float* __
   if (i >= (size_t)N * D) return;
   const int j = i / D, d = i % D;
   const float* e = E + (size_t)j * M * D + d;
-  const float s = cascade_sum_rows(e, M, D);
+  const float s = torch_order_sum_rows(e, M, D, d);
   const float den = (float)(M - 1);
   float* u = U + (size_t)j * M * D + d;
   for (int m = 0; m < M; ++m) u[(size_t)m * D] = __fdiv_rn(__fsub_rn(s, e[(size_t)m * D]), den);

@@ -3,7 +3,7 @@
 Tolerances (BASELINE.json north_star): embeddings 1e-3 per-vector L2-relative (bf16 recurrent GEMM, fp32
 accumulate); GE2E loss / dE / dw 1e-5 relative (fp32); db against the float64 oracle (the fp32
 reference itself is 1.7 % off there); EER bit-exact given identical similarity scores; LSTM parameter gradients
-(bf16 BPTT operands, no tolerance stated by north_star) 3e-2 per-tensor L2-relative.
+(bf16 BPTT operands, no tolerance stated by north_star) 1.2e-2 per-tensor L2-relative for weights, 3e-2 for biases.
 """
 import os
 
@@ -429,9 +429,9 @@ def test_embedder_saturated_weights(svb):
         with torch.no_grad():
             errs[terms] = emb_err(n(x).cpu().numpy(), g["emb"])
     print("embedding err, weights x2.5, recurrent terms 1/2/3:", errs)
-    # x2.5 weights amplify the bf16 rounding of W_hh (CPU emulation: 3.2e-3 / 1.0e-3 / 8e-6); the split-bf16
-    # recurrent GEMM restores the 1e-3 bar, the default single term stays within 5e-3 on this stress case
-    assert errs[3] < 1e-3 and errs[2] < 2e-3 and errs[1] < 5e-3, errs
+    # x2.5 weights amplify the operand rounding of W_hh; with fp16 operands (11-bit significands) the default single
+    # term holds north_star's 1e-3 bar on this stress case too (6.4e-4 measured), the residual terms stay inside it
+    assert errs[3] < 1e-3 and errs[2] < 1e-3 and errs[1] < 1e-3, errs
 
 
 def test_embedder_batch_independence_and_ragged_batch(svb, net):
@@ -466,8 +466,10 @@ def test_train_step_gradients(svb, net):
         assert abs(np.linalg.norm(go) - float(g[f"gnorm.{k}"])) < 2e-3 * float(g[f"gnorm.{k}"])   # oracle == reference
         errs[k] = rel_l2(p.grad.cpu().numpy(), go)
     print("per-tensor grad rel-L2:", {k: round(float(v), 4) for k, v in errs.items()})
+    # fp16 gate stash + bf16 dG / W^T operands (scripts/precision_study_bwd.py: weights 7e-3, biases 0.8-2.1e-2; the
+    # bf16 gate stash of round 1 gave 1.4e-2 / 2-9e-2)
     for k, e in errs.items():
-        assert e < (1e-1 if "bias" in k else 3e-2), (k, e)
+        assert e < (3e-2 if "bias" in k else 1.2e-2), (k, e)
     assert rel(crit.w.grad.item(), w.grad.item()) < 2e-2
 
 
@@ -485,6 +487,242 @@ def test_state_dict_roundtrip_and_cpu_module(svb):
         e2 = e_gpu_module(x.cuda()).cpu()
     assert e_cpu_module.device.type == "cpu"
     assert torch.equal(e_cpu_module, e2)
+
+
+def test_full_size_c2_parameter_gradients_vs_reference_library(svb, net):
+    """BASELINE configs[1] (64 speakers x 10 utterances x 160 frames): every parameter gradient of the full train step
+    against the reference's own library path on the CPU (nn.LSTM / nn.Linear / F.cosine_similarity autograd, float32:
+    oracle.embedder.LibraryEmbedder + library_ge2e_loss, the calls speech_embedder_net.py:19-49 makes)."""
+    xn = I.logmel(640, 160, seed=1234)
+    crit = svb.GE2ELoss("cuda")
+    net.zero_grad()
+    loss = crit(net(torch.tensor(xn).cuda()).reshape(64, 10, -1))
+    loss.backward()
+    torch.manual_seed(0)
+    ref = oemb.LibraryEmbedder()
+    assert all(torch.equal(a, b.cpu()) for a, b in zip(ref.state_dict().values(), net.state_dict().values()))
+    w = torch.tensor(10.0, requires_grad=True)
+    b = torch.tensor(-5.0, requires_grad=True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    lo = oemb.library_ge2e_loss(ref(torch.tensor(xn)).reshape(64, 10, -1), w, b)
+    lo.backward()
+    assert rel(loss.item(), lo.item()) < 1e-3
+    errs = {k: rel_l2(p.grad.cpu().numpy(), dict(ref.named_parameters())[k].grad.numpy()) for k, p in net.named_parameters()}
+    print("C2 per-tensor grad rel-L2:", {k: round(float(v), 4) for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e < (3e-2 if "bias" in k else 1.2e-2), (k, e)
+    assert rel(crit.w.grad.item(), w.grad.item()) < 2e-2
+
+
+def test_bptt_is_invariant_to_the_gradient_scale(svb, net):
+    """BPTT runs under a power-of-two scale taken from max |dL/dh_last| (csrc/lstm.cu grad_scale_kernel), so that the
+    fp16 split-K partials of the persistent kernel never see a trained model's tiny gradients (or a huge SUM loss) in
+    their subnormal / overflow range: gradients of c * loss are c * gradients -- bit for bit when c is a power of two,
+    within rounding for any c -- from 1e-9 to 1e+6, on the persistent and the per-frame path."""
+    from pytorch_speaker_verification_b200 import ops
+    x = torch.tensor(I.logmel(140, 40, seed=21)).cuda()
+    v = torch.tensor(np.random.RandomState(4).randn(140, 256).astype(np.float32)).cuda()
+
+    def grads(c):
+        net.zero_grad()
+        ((net(x) * v).sum() * c).backward()
+        return {k: p.grad.double().clone() for k, p in net.named_parameters()}
+
+    try:
+        for mode in (True, False):
+            ops.set_persistent_bwd(mode)
+            base = grads(1.0)
+            for c in (2.0 ** -24, 2.0 ** 17):
+                g = grads(c)
+                for k in base:
+                    assert torch.equal(g[k], base[k] * c), (mode, c, k)
+            for c in (1e-9, 1e-4, 1e3, 1e6):
+                g = grads(c)
+                for k in base:
+                    assert rel_l2(g[k].cpu().numpy(), (base[k] * c).cpu().numpy()) < 3e-3, (mode, c, k)
+    finally:
+        ops.set_persistent_bwd(True)
+    net.zero_grad()
+    (net(x) * 0.0).sum().backward()                          # zero upstream gradient: scale 1, gradients exactly 0
+    assert all(float(p.grad.abs().max()) == 0.0 for p in net.parameters())
+
+
+def test_second_backward_raises_and_repack(svb, net):
+    """BPTT consumes the stash in place: a second backward through the same forward raises instead of returning
+    garbage; weights changed behind autograd's back (``p.data``) are picked up after ``repack()``; a pending graph
+    keeps the weight shadow it was built with when the weights change before its backward."""
+    import copy
+    m = copy.deepcopy(net)
+    x = torch.tensor(I.logmel(12, 20, seed=7)).cuda()
+    e = m(x)
+    e.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        e.sum().backward()
+    with torch.no_grad():
+        e0 = m(x)
+        m.LSTM_stack.weight_hh_l1.data.mul_(1.5)              # bypasses the version counter
+        assert torch.equal(m(x), e0)                          # documented: not seen ...
+        m.repack()
+        e1 = m(x)
+        assert not torch.equal(e1, e0)                        # ... until repack()
+        m.LSTM_stack.weight_hh_l1.mul_(1.0 / 1.5)             # a tracked in-place update is seen by itself
+        assert emb_err(m(x).cpu().numpy(), e0.cpu().numpy()) < 1e-3
+    # a pending graph keeps its own weight shadow: a weight update re-packs into a FRESH buffer
+    m2 = copy.deepcopy(net)
+    ea = m2(x)
+    old = m2._cache.buf
+    old_ptr, snapshot = old.data_ptr(), old.clone()
+    with torch.no_grad():
+        m2.LSTM_stack.weight_hh_l2.add_(0.05)
+        m2(x)
+    assert m2._cache.buf.data_ptr() != old_ptr and torch.equal(old, snapshot)
+    del ea
+
+
+def test_module_device_round_trip_like_the_checkpoint_code(svb):
+    """train_speech_embedder.py:77-82: ``embedder_net.eval().cpu()`` -> ``torch.save(state_dict)`` ->
+    ``.to(device).train()``; the weight shadows follow the parameters across the moves."""
+    import io
+    torch.manual_seed(0)
+    m = svb.SpeechEmbedder().cuda()
+    x = torch.tensor(I.logmel(9, 30, seed=5)).cuda()
+    with torch.no_grad():
+        e0 = m(x)
+    m.eval().cpu()
+    buf = io.BytesIO()
+    torch.save(m.state_dict(), buf)
+    with torch.no_grad():
+        assert torch.equal(m(x.cpu()), e0.cpu())              # CPU-resident module, CPU input: computed on the GPU
+    m.to("cuda").train()
+    with torch.no_grad():
+        assert torch.equal(m(x), e0)
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    m(x).sum().backward()
+    opt.step()
+    with torch.no_grad():
+        e1 = m(x)
+    assert not torch.equal(e1, e0)
+    buf.seek(0)
+    m.load_state_dict(torch.load(buf))
+    with torch.no_grad():
+        assert torch.equal(m(x), e0)
+    # a module left on the CPU trains too: gradients arrive on the CPU parameters
+    mc = svb.SpeechEmbedder()
+    mc.load_state_dict(m.state_dict())
+    mc(x.cpu()).square().sum().backward()
+    m.zero_grad()
+    m(x).square().sum().backward()
+    for (k, a), b in zip(mc.named_parameters(), m.parameters()):
+        assert a.grad.device.type == "cpu" and torch.equal(a.grad, b.grad.cpu()), k
+
+
+def test_centroid_kernels_bit_exact(svb):
+    """utils.get_centroids / get_utterance_centroids (utils.py:27-29, 40-58) against the reference's float32 bit
+    patterns (tests/golden/centroids.npz), and the autograd of get_utterance_centroids."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_centroids import CASES, bits_checksum, case_input
+    g = load("centroids.npz")
+    for (N, M, D, seed) in CASES:
+        E = case_input(N, M, D, seed)
+        tag = f"{N}x{M}x{D}"
+        C = svb.get_centroids(torch.tensor(E, device="cuda")).cpu().numpy()
+        U = svb.utils.get_utterance_centroids(torch.tensor(E, device="cuda")).cpu().numpy()
+        assert (bits_checksum(C) == g[f"{tag}.C_sum"]).all(), tag
+        assert (bits_checksum(U) == g[f"{tag}.U_sum"]).all(), tag
+        np.testing.assert_array_equal(U.ravel()[g[f"{tag}.U_idx"]], g[f"{tag}.U_val"])
+    E = torch.tensor(case_input(7, 3, 16, 3), requires_grad=True)             # CPU in -> CPU out, differentiable
+    V = torch.tensor(np.random.RandomState(0).randn(7, 3, 16).astype(np.float32))
+    U = svb.utils.get_utterance_centroids(E)
+    assert U.device.type == "cpu"
+    (U * V).sum().backward()
+    want = (V.sum(dim=1, keepdim=True) - V) / 2.0
+    np.testing.assert_allclose(E.grad.numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        svb.utils.get_utterance_centroids(torch.randn(3, 1, 8))
+
+
+def test_torch_custom_ops_are_registered(svb, net):
+    """The C ABI is reachable as torch.ops.svb200.* (schema, CUDA kernel, fake kernel, autograd): direct calls and
+    torch.library.opcheck on the differentiable entry points."""
+    from pytorch_speaker_verification_b200 import ops
+    for name in ops.OP_NAMES:
+        assert hasattr(torch.ops.svb200, name), name
+    E = torch.tensor(I.ge2e_embeddings(6, 4, 32, "unit"), device="cuda")
+    C = torch.ops.svb200.centroids(E)
+    cos = torch.ops.svb200.cossim(E, C)
+    loss, per = torch.ops.svb200.calc_loss(10.0 * cos - 5.0)
+    o = oge2e.ge2e_fwd_bwd(E.cpu().numpy(), 10.0, -5.0)
+    assert rel(loss.item(), o["loss"]) < 1e-5
+    l2 = torch.ops.svb200.ge2e_loss(E, torch.tensor(10.0, device="cuda"), torch.tensor(-5.0, device="cuda"), 1, True)
+    assert rel(l2[0].item(), o["loss"]) < 1e-5 and rel(l2[1].cpu().numpy(), o["dE"]) < 1e-5
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.svb200.centroids(E.cpu())                   # no CPU kernel is registered
+    Er = E.clone().requires_grad_(True)
+    Cr = C.clone().requires_grad_(True)
+    w = torch.tensor(10.0, device="cuda", requires_grad=True)
+    b = torch.tensor(-5.0, device="cuda", requires_grad=True)
+    chk = torch.library.opcheck
+    chk(torch.ops.svb200.centroids.default, (Er,))
+    chk(torch.ops.svb200.utterance_centroids.default, (Er,))
+    chk(torch.ops.svb200.cossim.default, (Er, Cr))
+    chk(torch.ops.svb200.calc_loss.default, ((10.0 * cos - 5.0).detach().requires_grad_(True),))
+    chk(torch.ops.svb200.ge2e_loss.default, (Er, w, b, 1, True))
+    chk(torch.ops.svb200.eer_sweep.default, (cos.detach()[:, :2].contiguous(), torch.tensor([0.5, 0.7], device="cuda")))
+    chk(torch.ops.svb200.segment_mean.default, (E.reshape(24, 32), torch.tensor([0, 5, 24], dtype=torch.int32, device="cuda")))
+    # embedder: schema / fake / autograd registration (the backward consumes its stash, so the two-run AOT comparison
+    # of opcheck is left out for it)
+    x = torch.tensor(I.logmel(12, 20, seed=7)).cuda()
+    params = net._ordered_params()
+    packed = torch.ops.svb200.pack_weights([p.detach() for p in params[:12]], 40, 768, 3)
+    chk(torch.ops.svb200.embedder_fwd.default, (x, params, packed, 768, 3, True, 1),
+        test_utils=("test_schema", "test_autograd_registration", "test_faketensor"))
+    emb, ws = torch.ops.svb200.embedder_fwd(x, params, packed, 768, 3, True, 1)
+    with torch.no_grad():
+        assert torch.equal(emb, net(x))
+
+
+def test_overlapped_reducer_orders_reductions_before_autograd(svb, net):
+    """dist.OverlappedGradReducer with a stand-in "all-reduce" that doubles each bucket asynchronously on another
+    stream: the doubled values must be what autograd sees, whether it adopts the bucket views as p.grad
+    (set_to_none=True) or ADDS them to existing gradients (set_to_none=False / gradient accumulation)."""
+    from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
+    x = torch.tensor(I.logmel(70, 30, seed=3)).cuda()
+    side = torch.cuda.Stream()
+
+    class Work:
+        def __init__(self, ev):
+            self.ev = ev
+
+        def wait(self):
+            torch.cuda.current_stream().wait_event(self.ev)
+
+    def fake_all_reduce(t):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(20_000_000)                     # ~10 ms: a late reduction would be seen as x1
+            t.mul_(2.0)
+            ev = torch.cuda.Event()
+            ev.record()
+        return Work(ev)
+
+    net.zero_grad()
+    net(x).square().sum().backward()
+    base = [p.grad.clone() for p in net.parameters()]
+    red = OverlappedGradReducer(all_reduce=fake_all_reduce)
+    net.zero_grad(set_to_none=True)
+    with red:
+        net(x).square().sum().backward()
+    assert red.buckets == 4
+    for p, g in zip(net.parameters(), base):
+        assert torch.equal(p.grad, 2.0 * g)
+    for p in net.parameters():                                # existing gradients: autograd accumulates
+        p.grad = torch.ones_like(p)
+    with red:
+        net(x).square().sum().backward()
+    for p, g in zip(net.parameters(), base):
+        assert torch.equal(p.grad, 1.0 + 2.0 * g)
+    net.zero_grad()
 
 
 # ----------------------------------------------------------------------------------------------- optimizer tail

@@ -216,3 +216,23 @@ def test_front_end_oracle_properties():
     edges = ofe.mel_to_hz(np.linspace(ofe.hz_to_mel(0.0), ofe.hz_to_mel(8000.0), 42))
     band = int(np.argmax(S[:, 20]))
     assert edges[band] < 1000.0 < edges[band + 2]
+
+
+def test_centroid_functions_bit_level():
+    """utils.get_centroids / get_utterance_centroids (utils.py:27-29, 40-58): the oracle's operation-order restatement
+    reproduces the reference's float32 bit patterns, also where M leaves torch's sequential-sum regime."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_centroids import CASES, bits_checksum, case_input
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "centroids.npz"))
+    for (N, M, D, seed) in CASES:
+        E = case_input(N, M, D, seed)
+        tag = f"{N}x{M}x{D}"
+        C, U = ge2e.get_centroids_bitwise(E), ge2e.get_utterance_centroids_bitwise(E)
+        assert (bits_checksum(C) == g[f"{tag}.C_sum"]).all(), tag
+        assert (bits_checksum(U) == g[f"{tag}.U_sum"]).all(), tag
+        np.testing.assert_array_equal(U.ravel()[g[f"{tag}.U_idx"]], g[f"{tag}.U_val"])
+        if f"{tag}.U" in g:
+            np.testing.assert_array_equal(U, g[f"{tag}.U"])
+            np.testing.assert_array_equal(C, g[f"{tag}.C"])
+        np.testing.assert_allclose(U, ge2e.get_utterance_centroids(E.astype(np.float64)), rtol=2e-4, atol=2e-5)
