@@ -73,8 +73,8 @@ class FusedClipSGD:
                 nb = ctypes.c_size_t(0)
                 check(_lib.lib().svb_clip_sgd_workspace_bytes(ctypes.byref(nb)), "svb_clip_sgd_workspace_bytes")
                 self._ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-            # the op declares params / grads as mutated, so autograd's version counters advance (the packed
-            # fp16/bf16 weight shadows key on Parameter._version)
             self._norms = torch.ops.svb200.clip_sgd(params, grads, group, max_norm, self.lr, self.write_clipped_grads,
                                                     self._ws)
+        for p in params:                      # the packed fp16/bf16 weight shadows key on Parameter._version
+            torch.autograd.graph.increment_version(p)
         return self._norms
