@@ -1016,6 +1016,7 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     }
     bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last; bp.inv_scale = inv_scale;
     bp.trace = reinterpret_cast<long long*>(g_trace_bwd);
+    bp.trace_l = getenv("SVB_TRACE_LAYER") ? atoi(getenv("SVB_TRACE_LAYER")) : 1;
     bp.B = B; bp.T = T; bp.L = L; bp.H = H; bp.nt = nt;
     cudaMemsetAsync(w.dcnt, 0, w.bcnt_bytes, s);
     overlap = g_wgrad_overlap && (H % 256 == 0) && T >= 16 && nt <= 1024 && TB >= 4096 && (side = side_stream()) != nullptr;

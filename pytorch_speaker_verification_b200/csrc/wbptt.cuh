@@ -51,6 +51,7 @@ constexpr int kWbAccCol = 384;
 // Three in-place buffers (gates -> dG 2 x 8 KB boxes, dc) + two read-only buffers (c_t, c_{t-1}): the in-place tiles
 // are busy from their TMA load through the gate math until their TMA store has drained (load latency + math + store
 // ~ 5000 cycles), which with two buffers alone bounded the tile period.
+constexpr int kWbIo = 3;
 constexpr int kWbOffG = 0, kWbOffDc = 16384, kWbIoBytes = 24576;       // per in-place buffer
 constexpr int kWbOffCt = 0, kWbOffCp = 8192, kWbCBytes = 16384;        // per read-only buffer
 constexpr int kWbStgBytes = 3 * kWbIoBytes + 2 * kWbCBytes;            // 104 KB
@@ -78,6 +79,7 @@ struct __align__(64) WbParams {
   const float* dh_last;    // [B][H] dL/dh of the top layer's last frame (times the gradient scale, lstm.cu)
   const float* inv_scale;  // device scalar: 1 / gradient scale, applied to the bias gradients on the way out
   long long* trace;
+  int trace_l;             // debug: layer whose R(l, 0, 0) / X(l, 0, 0) CTAs are traced (env SVB_TRACE_LAYER, default 1)
   int B, T, L, H, nt;
 };
 
@@ -114,31 +116,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void st_cluster_u4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float2 half2_to_float2(uint32_t h) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&h));
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-
 template <int H>
 __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_constant__ WbParams p) {
   constexpr int NS = H / 32;                 // 32-unit slices per layer (= R CTAs per layer)
@@ -180,7 +157,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   const long long total = (long long)T * nt;
   const bool has_x = is_R && l + 1 < p.L;      // dX from the layer above arrives through its ring
   // debug trace: R(1, 0, 0) rows [0, nt), X(1, 0, 0) rows [nt, 2 nt): 16 clock64 stamps per tile of frame T/2
-  long long* const trace_cta = (p.trace && l == 1 && u == 0 && s == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+  long long* const trace_cta = (p.trace && l == p.trace_l && u == 0 && s == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
   const long long t_cta0 = clock64();
 
   if (threadIdx.x == 0) {
@@ -443,6 +420,13 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
               __syncwarp();
               if (lane == 0) mbar_arrive(&dep_free[d]);
             }
+#ifndef SVB_NO_RING_DISCARD
+            else {
+              // the warp's 4 KB of the dX tile have been consumed: drop the lines from L2 without write-back (the ring
+              // is read exactly once, from L2; see the gin ring of wlstm.cuh).  Lane -> (row of 512 bytes, 128-byte line)
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(xf - lane + (lane >> 2) * 32 + (lane & 3) * 8) : "memory");
+            }
+#endif
           } else {
             if (ps == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&dep_free[d]); }
             if (l == p.L - 1 && t == T - 1) {
@@ -550,41 +534,86 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       }
     }
   } else if (warp == kWbWarpStore && !is_R) {
-    // ------------------------------------------------------------------ signal warp (X): publish dX tiles
+    // ------------------------------------------------------------------ signal thread (X): publish dX tiles (lazily,
+    // two tiles in flight: see the R store thread below)
     if (lane == 0) {
+      bool pend = false;
+      unsigned* pflag = nullptr;
+      unsigned pval = 0;
       for (long long it = 0; it < total; ++it) {
         const int buf = (int)(it & 1);
+        const uint32_t upar = (uint32_t)((it >> 1) & 1);
         const int t = T - 1 - (int)(it / nt), j = (int)(it % nt);
-        mbar_wait(&x_done[buf], (uint32_t)((it >> 1) & 1));
+        if (pend && !mbar_test_wait(&x_done[buf], upar)) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
+          pend = false;
+        }
+        mbar_wait(&x_done[buf], upar);
         float* dst = ly.xring + (((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512) * 4;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg) + buf * 8192),
                      "n"(8192) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(&x_taken[buf]);
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.xcnt + ((size_t)l * NS + ns) * nt + j), "r"((unsigned)(it / nt + 1)) : "memory");
+        if (pend) {
+          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+          asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
+        }
+        pend = true;
+        pflag = p.xcnt + ((size_t)l * NS + ns) * nt + j;
+        pval = (unsigned)(it / nt + 1);
+      }
+      if (pend) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
       }
     }
   } else if (warp == kWbWarpStore && is_R) {
-    // ------------------------------------------------------------------ store + signal warp (R)
+    // ------------------------------------------------------------------ store + signal thread (R)
+    // The completion of a tile's TMA stores (cp.async.bulk.wait_group, needed before the release that publishes the
+    // tile) takes 3400-4700 cycles under load -- waited for tile by tile it was as long as the kernel's period.  A
+    // tile is therefore published LAZILY: if the next tile is already staged its stores are issued first and the
+    // thread then waits for the older group only (wait_group 1: two tiles in flight); if the next tile is not ready
+    // the pending one is completed and published at once, so a release never waits for a later tile (with one tile per
+    // frame the next frame cannot start before it).  The in-place buffer is handed back as soon as it has been read.
     if (elect_one()) {
+      bool pend = false;
+      unsigned* pflag = nullptr;
+      long long* ptr_tr = nullptr;
       long long it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
-          const int buf = (int)(it & 1);
-          const uint32_t upar = (uint32_t)((it >> 1) & 1);
-          const int b3 = (int)(it % 3);
-          mbar_wait(&stg_full[b3], (uint32_t)((it / 3) & 1));
+          const int b3 = (int)(it % kWbIo);
+          const uint32_t par3 = (uint32_t)((it / kWbIo) & 1);
+          if (pend && !mbar_test_wait(&stg_full[b3], par3)) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            red_release_add(pflag, 1u);      // release: see wlstm.cuh
+            if (ptr_tr) *ptr_tr = clock64();
+            pend = false;
+          }
+          mbar_wait(&stg_full[b3], par3);
           const uint8_t* sb = stg + b3 * kWbIoBytes;
           tma_store_3d(&ly.t_dg, sb + kWbOffG, ns * 128, j * kWbTile, t);
           tma_store_3d(&ly.t_dg, sb + kWbOffG + 8192, ns * 128 + 64, j * kWbTile, t);
           tma_store_3d(&ly.t_dc, sb + kWbOffDc, ns * 32, j * kWbTile, 0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&stg_free[b3]);
-          red_release_add(p.dcnt + l * nt + j, 1u);      // release: see wlstm.cuh
-          if (trace_cta && t == T / 2) trace_cta[j * 16 + 15] = clock64();
+          if (pend) {
+            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            red_release_add(pflag, 1u);
+            if (ptr_tr) *ptr_tr = clock64();
+          }
+          pend = true;
+          pflag = p.dcnt + l * nt + j;
+          ptr_tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 + 15 : nullptr;
         }
+      }
+      if (pend) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        red_release_add(pflag, 1u);
+        if (ptr_tr) *ptr_tr = clock64();
       }
     }
   }

@@ -94,6 +94,36 @@ struct __align__(64) WlstmParams {
 #define WL_ACC(var, ...) do { __VA_ARGS__; } while (0)
 #endif
 
+// vector shared-memory accesses by 32-bit address (explicit LDS/STS: pointers derived from the aligned dynamic-smem base
+// lose their address space and compile to generic LD/ST)
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 half2_to_float2(uint32_t h) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -447,17 +477,20 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (!is_R) {
-        // gin = W_ih x + bias, in fragment order: float4 (rows 4r..4r+3) of column `col` at [r][col]
+        // gin = W_ih x + bias, in fragment order: float4 (rows 4r..4r+3) of column `col` at [r][col].  The tile is
+        // staged in shared memory (P's staging buffers are otherwise unused) in exactly the ring's layout and leaves
+        // through ONE bulk copy issued by the signal thread, whose completion + release publishes it.  Direct global
+        // stores needed a gpu-scope fence in every epilogue thread before the flag (~2000 cycles in the chain of every
+        // tile: P, not R, set the pace of layers 1 and 2 -- 3550 cycles per tile against 3070 for layer 0).
+        mbar_wait(&gin_taken[buf], upar ^ 1);     // the bulk copy of tile it-2 has read this buffer
+        const uint32_t gs = sb_a + (uint32_t)(sub * 512 + col) * 16;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          gfrag[k * 128] = make_float4(a0[4 * k] + bias, a0[4 * k + 1] + bias, a0[4 * k + 2] + bias, a0[4 * k + 3] + bias);
-          gfrag[1024 + k * 128] = make_float4(a1[4 * k] + bias, a1[4 * k + 1] + bias, a1[4 * k + 2] + bias, a1[4 * k + 3] + bias);
+          sts_f4(gs + k * 2048, make_float4(a0[4 * k] + bias, a0[4 * k + 1] + bias, a0[4 * k + 2] + bias, a0[4 * k + 3] + bias));
+          sts_f4(gs + 16384 + k * 2048, make_float4(a1[4 * k] + bias, a1[4 * k + 1] + bias, a1[4 * k + 2] + bias, a1[4 * k + 3] + bias));
         }
-        // every thread completes its own stores at gpu scope (the 512 fences overlap; ONE fence in the signal warp
-        // after the barrier waited ~3500 cycles per tile for the whole CTA's 32 KB and was the limiter of P)
-        fence_acq_rel_gpu();
-        mbar_wait(&gin_taken[buf], upar ^ 1);     // the signal warp has consumed this barrier's previous phase
-        mbar_arrive(&gin_done[buf]);              // the signal warp publishes the tile
+        fence_proxy_async_smem();
+        mbar_arrive(&gin_done[buf]);              // the signal warp copies and publishes the tile
         WL_STAMP(13);
         continue;
       }
@@ -482,6 +515,19 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           WL_ACC(w2, mbar_wait(&stg_free[buf], upar ^ 1));    // staging buffer drained by the store warp
           WL_STAMP(11);
         }
+#ifndef SVB_NO_RING_DISCARD
+        if (ps == 1) {
+          // The gin tile has been consumed (both halves are in registers and have been used): drop its 32 lines of this
+          // warp from L2 WITHOUT write-back.  The ring is consumed from L2 a few microseconds after it is written and
+          // never read again, yet every dirty line was eventually written back to HBM: 3.8 GB per C2 step, as much as
+          // the whole BPTT stash (the part is power-capped: forward 1.5 % faster without that traffic).  Ordering: the
+          // ring slot is refilled only after this tile's h has been published, which follows this instruction through
+          // the staging barrier and the store thread's gpu-scope release.  Lane -> (half, k, 128-byte line of the
+          // warp's 512-byte row).
+          const float4* dl = gfrag - lane + ((lane >> 4) * 1024 + ((lane >> 2) & 3) * 128) + (lane & 3) * 8;
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(dl) : "memory");
+        }
+#endif
         if (p.ablate & 2) continue;
         if (p.training) {
           // gate stash [row][packed col] fp16 (see pack8_stash): two boxes of 64 columns, 128B-swizzled rows
@@ -547,48 +593,90 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       WL_STAMP(13);
     }
   } else if (warp == kWlWarpStore && !is_R) {
-    // ------------------------------------------------------------------ signal warp (P): publish gin tiles
+    // ------------------------------------------------------------------ signal thread (P): copy out + publish gin tiles
+    // The completion of a bulk store (cp.async.bulk.wait_group, needed before the release that publishes the tile)
+    // takes thousands of cycles under load.  A tile is therefore published LAZILY: if the next tile is already staged
+    // its copy is issued first and the thread then waits for the older group only (wait_group 1: two tiles in flight);
+    // if the next tile is not ready the pending one is completed and published at once, so a release never waits for
+    // a later tile (with one tile per frame the next frame cannot start before it).
     if (lane == 0) {
-      long long it = 0;
-      WL_FOR_TILES(t, j, it) {
-        {
-          WL_ACC(w0, mbar_wait(&gin_done[it & 1], (uint32_t)((it >> 1) & 1)));
-          mbar_arrive(&gin_taken[it & 1]);
-          st_relaxed(p.gcnt + ((size_t)l * NS + n) * nt + j, (unsigned)(t + 1));
+      int t = 0, j = 0, jc = 0, je = wl_chunk_end(0, nt);
+      bool pend = false;
+      unsigned* pflag = nullptr;
+      unsigned pval = 0;
+      for (long long it = 0; it < total; ++it, wl_advance(t, j, jc, je, T, nt)) {
+        const int buf = (int)(it & 1);
+        const uint32_t upar = (uint32_t)((it >> 1) & 1);
+        if (pend && !mbar_test_wait(&gin_done[buf], upar)) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
+          pend = false;
         }
+        WL_ACC(w0, mbar_wait(&gin_done[buf], upar));
+        float* dst = ly.gin + ((size_t)((t % kWlGinRing) * nt + j) * NS + n) * 8192;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                     "r"(smem_u32(stg) + buf * kWlStgBytes), "n"(32768) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging buffer may be refilled
+        mbar_arrive(&gin_taken[buf]);
+        if (pend) {
+          WL_ACC(w1, asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"));   // the older tile is written: release its flag
+          asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
+        }
+        pend = true;
+        pflag = p.gcnt + ((size_t)l * NS + n) * nt + j;
+        pval = (unsigned)(t + 1);
+      }
+      if (pend) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
       }
     }
   } else if (warp == kWlWarpStore && is_R) {
-    // ------------------------------------------------------------------ store + signal warp (R only)
-    if (elect_one()) {
-      long long it = 0;
-      WL_FOR_TILES(t, j, it) {
-        {
-          const int buf = (int)(it & 1);
-          const uint32_t upar = (uint32_t)((it >> 1) & 1);
-          WL_ACC(w0, mbar_wait(&stg_full[buf], upar));
-          long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
-          WL_STAMP(14);
-          const uint8_t* sb = stg + buf * kWlStgBytes;
-          const int row0 = j * kWlTile;
-          tma_store_3d(&ly.t_h16_st, sb + kWlOffH16, n * 32, row0, t + 1);
-          tma_store_3d(&ly.t_c, sb + kWlOffC, n * 32, row0, p.training ? t + 1 : ((t + 1) & 1));
-          if (p.training) {
-            tma_store_3d(&ly.t_hbf_st, sb + kWlOffHbf, n * 32, row0, t + 1);
-            tma_store_3d(&ly.t_gates, sb + kWlOffG, n * 128, row0, t);
-            tma_store_3d(&ly.t_gates, sb + kWlOffG + 8192, n * 128 + 64, row0, t);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          // complete (implies the staging buffer has been read), then a RELEASE increment publishes the tile.  The
-          // release is required: with a relaxed increment other CTAs' TMA loads read stale rows of the tile (found
-          // with a NaN-poisoned workspace, tests/test_gpu_parity.py::test_persistent_kernel_no_stale_reads).  One
-          // fence is enough and costs nothing at the current period; proxy fence + __threadfence + release together
-          // cost ~3000 cycles per tile and made this warp the limiter.
-          WL_ACC(w1, asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"));
-          mbar_arrive(&stg_free[buf]);
-          WL_ACC(w2, red_release_add(p.hcnt + l * nt + j, 1u));
-          WL_STAMP(15);
+    // ------------------------------------------------------------------ store + signal thread (R only): lazy publish,
+    // two tiles in flight (see the P signal thread above)
+    if (lane == 0) {
+      int t = 0, j = 0, jc = 0, je = wl_chunk_end(0, nt);
+      bool pend = false;
+      unsigned* pflag = nullptr;
+      for (long long it = 0; it < total; ++it, wl_advance(t, j, jc, je, T, nt)) {
+        const int buf = (int)(it & 1);
+        const uint32_t upar = (uint32_t)((it >> 1) & 1);
+        if (pend && !mbar_test_wait(&stg_full[buf], upar)) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          red_release_add(pflag, 1u);
+          pend = false;
         }
+        WL_ACC(w0, mbar_wait(&stg_full[buf], upar));
+        long long* tr = (trace_cta && t == T / 2) ? trace_cta + j * 16 : nullptr;
+        WL_STAMP(14);
+        const uint8_t* sb = stg + buf * kWlStgBytes;
+        const int row0 = j * kWlTile;
+        tma_store_3d(&ly.t_h16_st, sb + kWlOffH16, n * 32, row0, t + 1);
+        tma_store_3d(&ly.t_c, sb + kWlOffC, n * 32, row0, p.training ? t + 1 : ((t + 1) & 1));
+        if (p.training) {
+          tma_store_3d(&ly.t_hbf_st, sb + kWlOffHbf, n * 32, row0, t + 1);
+          tma_store_3d(&ly.t_gates, sb + kWlOffG, n * 128, row0, t);
+          tma_store_3d(&ly.t_gates, sb + kWlOffG + 8192, n * 128 + 64, row0, t);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&stg_free[buf]);          // the staging buffer has been read: the epilogue may refill it
+        // complete, then a RELEASE increment publishes the tile.  The release is required: with a relaxed increment
+        // other CTAs' TMA loads read stale rows of the tile (found with a NaN-poisoned workspace,
+        // tests/test_gpu_parity.py::test_persistent_kernel_no_stale_reads).  One fence is enough; proxy fence +
+        // __threadfence + release together cost ~3000 cycles per tile.
+        if (pend) {
+          WL_ACC(w1, asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"));
+          WL_ACC(w2, red_release_add(pflag, 1u));
+        }
+        pend = true;
+        pflag = p.hcnt + l * nt + j;
+        WL_STAMP(15);
+      }
+      if (pend) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        red_release_add(pflag, 1u);
       }
     }
   }
