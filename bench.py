@@ -511,17 +511,18 @@ def main():
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     reducer = None
-    if world > 1 and os.environ.get("SVB_ALLREDUCE_OVERLAP", "0") == "1":
+    if world > 1 and os.environ.get("SVB_ALLREDUCE_OVERLAP", "1") != "0":
+        # default at N > 1: the gradient all-reduce runs in four buckets started from inside backward, beside the
+        # remaining weight-gradient GEMMs (SVB_ALLREDUCE_OVERLAP=0: one all-reduce after backward)
         from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
         reducer = OverlappedGradReducer()
 
     def fwd_bwd(x):
         emb = net(x)
         loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
-        if reducer is not None:               # SVB_ALLREDUCE_OVERLAP=1: bucketed all-reduce started from inside backward
+        if reducer is not None:               # bucketed all-reduce started from inside backward
             with reducer:
                 loss.backward()
-            reducer.finish()
             return loss
         loss.backward()
         if world > 1:
@@ -580,6 +581,36 @@ def main():
             p.grad = None
         return fwd_bwd(x_dev)
 
+    def dist_check():
+        """N ranks == 1 rank: the sharded step (speakers split over the ranks, d-vector all-gather, global GE2E, SUM
+        all-reduce of the gradients) against the same global batch run by rank 0 alone (40 frames to keep it short)."""
+        Tc = 40
+        xs = torch.tensor(I.logmel(B, Tc, seed=4321 + rank)).to(dev)
+        for p in list(params) + [crit.w, crit.b]:
+            p.grad = None
+        loss = fwd_bwd(xs)
+        torch.cuda.synchronize()
+        sharded = [p.grad.clone() for p in params] + [crit.w.grad.clone()]
+        x_all = torch.empty(world * B, Tc, NMELS, device=dev)
+        dist.all_gather_into_tensor(x_all, xs)
+        res = None
+        if rank == 0:
+            for p in list(params) + [crit.w, crit.b]:
+                p.grad = None
+            l1 = crit(net(x_all).reshape(world * N_SPK, M_UTT, PROJ))
+            l1.backward()
+            torch.cuda.synchronize()
+            single = [p.grad for p in params] + [crit.w.grad]
+            errs = [float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)) for a, b in zip(sharded, single)]
+            lerr = abs(float(loss) - float(l1)) / abs(float(l1))
+            res = {"ranks": world, "speakers": world * N_SPK, "frames": Tc, "loss_rel_err": lerr,
+                   "grad_rel_l2_max": max(errs), "ok": bool(lerr < 1e-5 and max(errs) < 5e-3),
+                   "what": "sharded step (all-gather + global GE2E + SUM all-reduce) vs rank 0 alone on the global batch"}
+        for p in list(params) + [crit.w, crit.b]:
+            p.grad = None
+        barrier()
+        return res
+
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if rank == 0 else None
     ms_value = timed(value_step, args.steps, args.warmup)
     ms_e2e = timed(full_step, args.steps, args.warmup)
@@ -606,6 +637,7 @@ def main():
     phases = phase_profile(value_step)          # every rank: the step contains collectives
     barrier()
     loss_val = float(loss_host)
+    check = dist_check() if world > 1 else None
     launch_count = count_launches(L, value_step, torch)      # one extra, untimed step seen through CUPTI
     extra = secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world, args.extract_utts)
     extra["e2e_with_prefetch_and_fused_clip_sgd"] = {
@@ -681,6 +713,8 @@ def main():
             "secondary": extra,
             "loss": loss_val,
         }
+        if check is not None:
+            line["dist_check"] = check
         accounted = sum(phases.values())
         line["phases_ms"]["unattributed"] = ms_value - accounted
         line["phases_note"] = ("phases_ms are CUDA-event brackets inside svb_embedder_forward/backward; `unattributed` = "

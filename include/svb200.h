@@ -126,6 +126,17 @@ int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, con
              const float* dcos, const float* gscale, float* cos_out, float* per_out, float* loss_out, float* dE,
              float* dCext, float* dw, float* db, void* workspace, size_t workspace_bytes, int fused, void* stream);
 
+/* Row shard of a global GE2E batch (new: multi-GPU, one process per GPU; the reference is single-device).  E: the M
+ * utterances of speakers [col0, col0 + N_local) of a batch of Nc speakers; C (Nc, D): all centroids (utils.py:27-29 of
+ * every rank's shard, all-gathered).  Same arithmetic as svb_ge2e on the global batch restricted to these rows, with the
+ * rows' own column col0 + j as the leave-one-out diagonal (utils.py:91,113).  loss_out / dw / db: the shard's partial
+ * sums; dE (N_local, M, D): without the path through the rows' own centroid; dC (Nc, D): the shard's contribution to
+ * every centroid's gradient.  The caller sums loss, dw, db, dC over the ranks and adds dC_total[col0 + j] / M to every
+ * utterance of speaker j (svb_centroids_bwd). */
+int svb_ge2e_rows(const float* E, const float* C, int N_local, int M, int D, int Nc, int col0, const float* w,
+                  const float* b, const float* gscale, float* per_out, float* loss_out, float* dE, float* dC, float* dw,
+                  float* db, void* workspace, size_t workspace_bytes, void* stream);
+
 /* utils.get_centroids (utils.py:27-29) and its backward. */
 int svb_centroids(const float* E, float* C, int N, int M, int D, void* stream);
 int svb_centroids_bwd(const float* dC, float* dE, int N, int M, int D, void* stream);

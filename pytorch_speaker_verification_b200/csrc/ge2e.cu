@@ -40,6 +40,7 @@ struct Ge2eArgs {
   const float* dcos;     // upstream gradient of the cosine matrix [N, M, Nc] (get_cossim backward) or null
   const float* gscale;   // device scalar multiplying all gradients (upstream dL) or null (= 1)
   int N, M, D, Nc;
+  int col0;              // column of the centroid matrix that belongs to speaker 0 of E (row shard of a global batch)
   int need_grad;
   int psplit, prows;     // P = A_off^T E^ is accumulated over psplit slices of prows embedding rows
   // outputs (nullable)
@@ -241,7 +242,7 @@ __device__ void phase_b2(const Ge2eArgs& a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float w = a.w ? *a.w : 0.f, b = a.b ? *a.b : 0.f;
   for (int row = blockIdx.x * kWarps + warp; row < NM; row += gridDim.x * kWarps) {
-    const int j = row / M;
+    const int j = row / M + a.col0;                     // this row's own column ("diagonal")
     float* t = a.cosm + (size_t)row * Nc;
     const float cd = a.cosd[row];
     if (lane == 0 && j < Nc) t[j] = cd;                 // diagonal overwrite (utils.py:113)
@@ -895,16 +896,17 @@ extern "C" int svb_ge2e_trace_offset(int N, int M, int D, int Nc, size_t* offset
   return SVB_OK;
 }
 
-extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w,
-                        const float* b, const float* dcos, const float* gscale, float* cos_out, float* per_out,
-                        float* loss_out, float* dE, float* dCext, float* dw, float* db, void* workspace,
-                        size_t workspace_bytes, int fused, void* stream) {
+static int ge2e_impl(const float* E, const float* Cext, int N, int M, int D, int Nc, int col0, const float* w,
+                     const float* b, const float* dcos, const float* gscale, float* cos_out, float* per_out,
+                     float* loss_out, float* dE, float* dCext, float* dw, float* db, void* workspace,
+                     size_t workspace_bytes, int fused, void* stream) {
   if (!E || N < 1 || M < 2 || D < 1 || !workspace) { set_error("svb_ge2e: bad argument (M must be >= 2)", cudaSuccess); return SVB_ERR_ARG; }
+  if (col0 < 0 || (col0 > 0 && (!Cext || col0 + N > Nc))) { set_error("svb_ge2e: row shard outside the centroid matrix", cudaSuccess); return SVB_ERR_ARG; }
   if (!Cext && Nc != N) { set_error("svb_ge2e: Nc must equal N without foreign centroids", cudaSuccess); return SVB_ERR_ARG; }
   if ((w == nullptr) != (b == nullptr)) return SVB_ERR_ARG;
   Ge2eArgs a{};
   a.E = E; a.Cext = Cext; a.w = w; a.b = b; a.dcos = dcos; a.gscale = gscale;
-  a.N = N; a.M = M; a.D = D; a.Nc = Nc;
+  a.N = N; a.M = M; a.D = D; a.Nc = Nc; a.col0 = col0;
   a.need_grad = (dE != nullptr) ? 1 : 0;
   if (a.need_grad && !w && !dcos) { set_error("svb_ge2e: gradient requested without w/b or dcos", cudaSuccess); return SVB_ERR_ARG; }
   a.cos_out = cos_out; a.per_out = per_out; a.loss_out = loss_out; a.dE = dE; a.dCext = dCext; a.dw = dw; a.db = db;
@@ -977,13 +979,19 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(kST); cfg.dynamicSmemBytes = sm; cfg.stream = s;
       cudaLaunchAttribute at[2];
-      if (CL > 1) {       // plain cluster launch + the kernel's own grid barrier
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (CL > 1) {
+        // cooperative cluster launch: the kernel's own grid barrier spins on all 2N CTAs, so their co-residency must be
+        // guaranteed by the driver (another stream's kernel -- a second GE2E launch, NCCL -- may hold SMs).  Nsight
+        // Compute refuses cooperative + cluster launches: profiling runs set SVB_PLAIN_CLUSTER_LAUNCH=1.
+        static const bool plain = getenv("SVB_PLAIN_CLUSTER_LAUNCH") != nullptr;
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+        cfg.numAttrs = plain ? 1 : 2;
       } else {
         at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
       }
-      cfg.attrs = at; cfg.numAttrs = 1;
       void* params[] = {&a};
       cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
       if (e == cudaSuccess) return SVB_OK;
@@ -1011,6 +1019,28 @@ extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, 
     if (e != cudaSuccess) { set_error("svb_ge2e: launch", e); return SVB_ERR_CUDA; }
   }
   return SVB_OK;
+}
+
+extern "C" int svb_ge2e(const float* E, const float* Cext, int N, int M, int D, int Nc, const float* w,
+                        const float* b, const float* dcos, const float* gscale, float* cos_out, float* per_out,
+                        float* loss_out, float* dE, float* dCext, float* dw, float* db, void* workspace,
+                        size_t workspace_bytes, int fused, void* stream) {
+  return ge2e_impl(E, Cext, N, M, D, Nc, 0, w, b, dcos, gscale, cos_out, per_out, loss_out, dE, dCext, dw, db, workspace,
+                   workspace_bytes, fused, stream);
+}
+
+// Row shard of a global GE2E batch (multi-GPU, SURVEY.md section 8e design A): E holds the M utterances of the N_local
+// speakers [col0, col0 + N_local) of a batch of Nc speakers whose centroids C (Nc, D) have been gathered from all
+// ranks.  Every row is scored against all Nc centroids, with its own column col0 + j replaced by the leave-one-out
+// cosine (utils.py:91,113).  Outputs: the shard's part of the loss / dw / db (to be summed over the ranks), dE of the
+// shard's rows WITHOUT the path through their own centroid, and dC (Nc, D): this shard's contribution to the gradient
+// of every centroid (summed over the ranks, row j of the total is then spread over speaker j's utterances as dC_j / M).
+extern "C" int svb_ge2e_rows(const float* E, const float* C, int N_local, int M, int D, int Nc, int col0, const float* w,
+                             const float* b, const float* gscale, float* per_out, float* loss_out, float* dE, float* dC,
+                             float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!C || !w || !b) { set_error("svb_ge2e_rows: centroids, w and b are required", cudaSuccess); return SVB_ERR_ARG; }
+  return ge2e_impl(E, C, N_local, M, D, Nc, col0, w, b, nullptr, gscale, nullptr, per_out, loss_out, dE, dC, dw, db,
+                   workspace, workspace_bytes, 2, stream);
 }
 
 // Sum over the utterance axis in the order torch's CPU sum kernel uses for this layout (reduction over a strided

@@ -997,7 +997,9 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   };
   if (g_persistent_bwd && H == 768 && L <= 3) {
     const int num_sms = device_sm_count();
-    use_wbptt = 4 * (2 * L - 1) * (H / 128) + 16 <= num_sms;    // clusters of 4 strand up to 16 SMs
+    // all (2L - 1) * H/128 clusters of 4 must be co-resident: ask the occupancy calculator (clusters of 4 strand SMs
+    // at GPC boundaries: 33 fit the 148 SMs of a B200), else the per-frame path below
+    use_wbptt = num_sms >= 4 * (2 * L - 1) * (H / 128) && wbptt_max_clusters<768>() >= (2 * L - 1) * (H / 128);
   }
   if (use_wbptt) {
     // ---- BPTT of the whole stack (recurrent products, dX products, gate backward) in one persistent kernel

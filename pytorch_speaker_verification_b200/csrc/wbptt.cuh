@@ -635,6 +635,29 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   if (p.trace && threadIdx.x == 0) p.trace[2 * nt * 16 + blockIdx.x] = clock64() - t_cta0;
 }
 
+// Largest number of 4-CTA clusters of the kernel that can be co-resident on the current device (0 on error).
+template <int H>
+static int wbptt_max_clusters() {
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device_index();
+  if (!cached[dev]) {
+    auto kern = wbptt_kernel<H>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWbSmem) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(kWbThreads);
+    cfg.dynamicSmemBytes = kWbSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cached[dev] = n > 0 ? n : -1;
+  }
+  return cached[dev] > 0 ? cached[dev] : 0;
+}
+
 template <int H>
 static int launch_wbptt(WbParams& p, cudaStream_t s) {
   auto kern = wbptt_kernel<H>;
@@ -654,13 +677,13 @@ static int launch_wbptt(WbParams& p, cudaStream_t s) {
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  // Plain cluster launch by default: Nsight Compute refuses the cooperative + cluster combination (LaunchFailed), and
-  // the 30 clusters are co-resident anyway (one 640-thread, 218 KB CTA per SM; at most 33 four-CTA clusters fit the
-  // 148 SMs) as long as no other spinning kernel holds SMs.  Kernels of the same stream run before / after this one;
-  // CTAs of unrelated kernels on other streams finish and free their SMs.  A dependency that never arrives traps
-  // after the bounded spins instead of hanging.  SVB_COOPERATIVE_BPTT=1 adds the cooperative guarantee.
-  static const bool coop = getenv("SVB_COOPERATIVE_BPTT") != nullptr;
-  cfg.numAttrs = coop ? 2 : 1;
+  // Cooperative cluster launch: the driver guarantees that all 30 clusters are co-resident (the kernel's flag protocol
+  // spins on other CTAs' progress), whatever else is running -- NCCL kernels of an overlapped all-reduce, a second
+  // stream.  Nsight Compute refuses the cooperative + cluster combination (LaunchFailed), so profiling runs set
+  // SVB_PLAIN_CLUSTER_LAUNCH=1: a plain cluster launch, safe only while nothing else holds SMs (one 640-thread, 218 KB
+  // CTA per SM; the occupancy query in svb_embedder_backward has checked that the clusters fit an empty device).
+  static const bool plain = getenv("SVB_PLAIN_CLUSTER_LAUNCH") != nullptr;
+  cfg.numAttrs = plain ? 1 : 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) { set_error("wbptt: cluster launch", e); return SVB_ERR_CUDA; }
   return SVB_OK;

@@ -1,9 +1,10 @@
 """Multi-GPU GE2E: one process per GPU, speakers sharded across ranks.
 
 The LSTM / projection / L2 norm are independent per utterance (pure data parallel, no exchange).  GE2E couples
-speakers only through the centroids, so the one forward exchange is an all-gather of the (N_local*M, D) d-vectors;
-every rank then evaluates the fused GE2E kernel on the global (N, M, D) batch and keeps its own slice of dL/dE
-(design "B": no backward exchange for the loss; w.grad/b.grad are identical on every rank).  Parameter gradients are
+speakers only through the centroids: by default (design "A") the ranks all-gather their (N_local, D) centroids, score
+their own rows against all of them and all-reduce the centroid gradients; design "B" (mode="gather") all-gathers the
+(N_local*M, D) d-vectors and lets every rank evaluate the whole global batch.  Either way w.grad/b.grad are identical on
+every rank.  Parameter gradients are
 all-reduced with SUM -- not mean -- because the reference loss is a sum over rows (utils.py:131).
 
 The reference has no distributed code at all; this module is new functionality behind the same GE2ELoss object.
@@ -26,7 +27,14 @@ def _fused_loss_and_grads(E, w, b):
     return torch.ops.svb200.ge2e_loss(E, w, b, 1, True)
 
 
+def _rows_loss_and_grads(E_local, C_all, w, b, col0):
+    """-> (reduction buffer [dC (N*D) | loss, dw, db] of this rank's rows, dE of the rows without the centroid path)"""
+    return torch.ops.svb200.ge2e_rows(E_local, C_all, w, b, int(col0))
+
+
 class _GlobalGE2EFn(torch.autograd.Function):
+    """Design "B": all-gather of the d-vectors, every rank evaluates the whole global batch and keeps its slice."""
+
     @staticmethod
     def forward(ctx, local_emb, w, b, group, compute):
         world = dist.get_world_size(group)
@@ -48,18 +56,56 @@ class _GlobalGE2EFn(torch.autograd.Function):
         return dE, dw, db, None, None
 
 
+class _ShardedGE2EFn(torch.autograd.Function):
+    """Design "A" (SURVEY.md section 8e): the speakers of other ranks enter a rank's rows only through their centroids,
+    so the forward exchange is an all-gather of the (N_local, D) centroids (65 KB per rank at 64 x 256 instead of the
+    655 KB of d-vectors), every rank scores ITS rows against all N centroids (1/world of the work instead of all of
+    it), and one SUM all-reduce of [dC (N, D) | loss, dw, db] (524 KB at N = 512) returns the centroid gradients, which
+    each rank spreads over its own utterances (dC_j / M)."""
+
+    @staticmethod
+    def forward(ctx, local_emb, w, b, group, compute_rows):
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        Nl, M, D = local_emb.shape
+        E = local_emb.contiguous()
+        C_local = E.mean(dim=1) if compute_rows is not _rows_loss_and_grads else torch.ops.svb200.centroids(E)
+        C_all = torch.empty(world * Nl, D, dtype=E.dtype, device=E.device)
+        dist.all_gather_into_tensor(C_all, C_local.contiguous(), group=group)
+        red, dE = compute_rows(E, C_all, w.detach(), b.detach(), rank * Nl)
+        dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+        N = world * Nl
+        dC_own = red[:N * D].view(N, D)[rank * Nl:(rank + 1) * Nl]
+        if dE.device.type == "cuda":
+            dE = dE + torch.ops.svb200.centroids_bwd(dC_own.contiguous(), M)
+        else:
+            dE = dE + (dC_own / M).unsqueeze(1)
+        ctx.save_for_backward(dE, red[N * D + 1].clone(), red[N * D + 2].clone())
+        return red[N * D].clone()
+
+    backward = _GlobalGE2EFn.backward
+
+
 class GlobalGE2ELoss(torch.nn.Module):
     """Wraps a GE2ELoss so that ``forward(local_embeddings (N_local, M, D))`` returns the loss of the GLOBAL batch
-    (the same number on every rank) and back-propagates this rank's slice of dL/dE."""
+    (the same number on every rank) and back-propagates this rank's slice of dL/dE.
 
-    def __init__(self, criterion, group=None, compute=None):
+    ``mode="rows"`` (default): centroid all-gather + this rank's rows against all centroids + one all-reduce of the
+    centroid gradients (design A); ``mode="gather"``: d-vector all-gather, every rank evaluates the global batch
+    (design B, round 1).  ``compute`` injects the arithmetic (host-logic tests on CPU / gloo)."""
+
+    def __init__(self, criterion, group=None, compute=None, mode="rows"):
         super().__init__()
+        if mode not in ("rows", "gather"):
+            raise ValueError(mode)
         self.criterion = criterion
         self.group = group
-        self.compute = compute or _fused_loss_and_grads
+        self.mode = mode
+        self.compute = compute or (_rows_loss_and_grads if mode == "rows" else _fused_loss_and_grads)
 
     def forward(self, local_embeddings):
-        return _GlobalGE2EFn.apply(local_embeddings, self.criterion.w, self.criterion.b, self.group, self.compute)
+        fn = _ShardedGE2EFn if self.mode == "rows" else _GlobalGE2EFn
+        return fn.apply(local_embeddings, self.criterion.w, self.criterion.b, self.group, self.compute)
 
 
 def allreduce_gradients(params, group=None):

@@ -366,6 +366,34 @@ _op("ge2e_loss(Tensor E, Tensor w, Tensor b, int fused, bool need_grad) -> (Tens
     _ge2e_loss, _ge2e_loss_fake)
 
 
+def _ge2e_rows(E: torch.Tensor, C: torch.Tensor, w: torch.Tensor, b: torch.Tensor, col0: int
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    N, M, D = (int(v) for v in E.shape)
+    Nc = int(C.shape[0])
+    dev = E.device
+    with torch.cuda.device(dev):
+        nbytes = _sz(0)
+        check(_lib.lib().svb_ge2e_workspace_bytes(N, M, D, Nc, ctypes.byref(nbytes)), "svb_ge2e_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        # one buffer for everything that is summed over the ranks: dC (Nc, D), then loss, dw, db
+        red = torch.empty(Nc * D + 3, dtype=torch.float32, device=dev)
+        dE = torch.empty(N, M, D, dtype=torch.float32, device=dev)
+        base = red.data_ptr()
+        f = lambda off: ctypes.c_void_p(base + 4 * off)
+        check(_lib.lib().svb_ge2e_rows(ptr(E.contiguous()), ptr(C.contiguous()), N, M, D, Nc, int(col0), ptr(w.contiguous()),
+                                       ptr(b.contiguous()), None, None, f(Nc * D), ptr(dE), f(0), f(Nc * D + 1),
+                                       f(Nc * D + 2), ptr(ws), _sz(nbytes.value), stream_ptr(dev)), "svb_ge2e_rows")
+    return red, dE
+
+
+def _ge2e_rows_fake(E, C, w, b, col0):
+    return E.new_empty(C.shape[0] * C.shape[1] + 3), torch.empty_like(E)
+
+
+# row shard of a global batch against all-gathered centroids: (reduction buffer [dC | loss, dw, db], dE of the shard)
+_op("ge2e_rows(Tensor E, Tensor C, Tensor w, Tensor b, int col0) -> (Tensor, Tensor)", _ge2e_rows, _ge2e_rows_fake)
+
+
 def _scale3(dE: torch.Tensor, dw: torch.Tensor, db: torch.Tensor, g: torch.Tensor
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     dE, dw, db = dE.clone(), dw.clone(), db.clone()
@@ -684,6 +712,6 @@ def _logmel(y: torch.Tensor, window: torch.Tensor, twiddle: torch.Tensor, mel_w:
 _op("logmel(Tensor y, Tensor window, Tensor twiddle, Tensor mel_w, int hop, int w0, int w1) -> Tensor", _logmel,
     lambda y, window, twiddle, mel_w, hop, w0, w1: y.new_empty(mel_w.shape[0], 1 + y.numel() // hop))
 
-OP_NAMES = ["pack_weights", "embedder_fwd", "embedder_bwd", "ge2e_loss", "scale3", "centroids", "centroids_bwd",
+OP_NAMES = ["pack_weights", "embedder_fwd", "embedder_bwd", "ge2e_loss", "ge2e_rows", "scale3", "centroids", "centroids_bwd",
             "utterance_centroids", "cossim", "cossim_bwd", "calc_loss", "calc_loss_bwd", "eer_counts", "eer_sweep",
             "eer_finish", "dvector_windows", "segment_mean", "clip_sgd", "logmel"]

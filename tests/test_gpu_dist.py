@@ -35,14 +35,27 @@ def _worker(rank, world, port, out):
     x = torch.tensor(I.logmel(N * M, T, seed=42)).reshape(N, M, T, 40)
     lo, hi = speaker_shard(N, rank, world)
     emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
-    loss = GlobalGE2ELoss(crit)(emb.reshape(hi - lo, M, -1))
+    loss = GlobalGE2ELoss(crit)(emb.reshape(hi - lo, M, -1))          # default: centroid all-gather + row shards
     loss.backward()
     allreduce_gradients(list(net.parameters()))
     out[rank] = (loss.item(), net.LSTM_stack.weight_hh_l1.grad.cpu(), net.projection.weight.grad.cpu(),
                  crit.w.grad.item())
+    # design B (d-vector all-gather, global batch on every rank) gives the same step
+    first = [p.grad.clone() for p in net.parameters()]
+    w_first = crit.w.grad.clone()
+    net.zero_grad()
+    crit.zero_grad()
+    emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
+    lossB = GlobalGE2ELoss(crit, mode="gather")(emb.reshape(hi - lo, M, -1))
+    lossB.backward()
+    allreduce_gradients(list(net.parameters()))
+    assert abs(lossB.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert abs(crit.w.grad.item() - w_first.item()) < 1e-4 * abs(w_first.item())
+    for p, r in zip(net.parameters(), first):
+        assert torch.allclose(p.grad, r, rtol=2e-3, atol=1e-6)
     # the same step with the bucketed all-reduce started from inside backward: identical sums
     from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
-    ref = [p.grad.clone() for p in net.parameters()]
+    ref = first                                  # (same GE2E mode: the sums must be bit-identical)
     net.zero_grad()
     crit.zero_grad()
     emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
@@ -50,7 +63,6 @@ def _worker(rank, world, port, out):
     reducer = OverlappedGradReducer()
     with reducer:
         loss2.backward()
-    reducer.finish()
     torch.cuda.synchronize()
     assert reducer.buckets == 4
     for p, r in zip(net.parameters(), ref):

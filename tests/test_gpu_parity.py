@@ -642,6 +642,32 @@ def test_centroid_kernels_bit_exact(svb):
         svb.utils.get_utterance_centroids(torch.randn(3, 1, 8))
 
 
+@pytest.mark.parametrize("N,M,D,shards", [(8, 4, 32, 2), (64, 10, 256, 8), (512, 10, 256, 8), (12, 3, 20, 3)])
+def test_ge2e_row_shards_sum_to_the_global_batch(svb, N, M, D, shards):
+    """svb_ge2e_rows (multi-GPU design A: a rank's rows against the all-gathered centroids) on one GPU: the shards'
+    partial losses / dw / db / centroid gradients sum to the global batch's (fp64 closed form), and
+    dE_rows + dC_total[own speaker] / M is the global dL/dE."""
+    Enp = I.ge2e_embeddings(N, M, D, "clustered" if N >= 64 else "raw")
+    o = oge2e.ge2e_fwd_bwd(Enp.astype(np.float64), 10.0, -5.0)
+    E = torch.tensor(Enp, device="cuda")
+    w = torch.tensor(10.0, device="cuda")
+    b = torch.tensor(-5.0, device="cuda")
+    C = svb.get_centroids(E)
+    nl = N // shards
+    reds, dEs = [], []
+    for r in range(shards):
+        red, dE = torch.ops.svb200.ge2e_rows(E[r * nl:(r + 1) * nl].contiguous(), C, w, b, r * nl)
+        reds.append(red.double())
+        dEs.append(dE)
+    red = torch.stack(reds).sum(dim=0)
+    dC = red[:N * D].view(N, D).float()
+    assert rel(red[N * D].item(), o["loss"]) < 1e-5
+    assert rel(red[N * D + 1].item(), o["dw"]) < 1e-5
+    assert rel(red[N * D + 2].item(), o["db"]) < 2e-3
+    dE = torch.cat(dEs) + torch.ops.svb200.centroids_bwd(dC.contiguous(), M)
+    assert rel(dE.cpu().numpy(), o["dE"]) < 1e-5
+
+
 def test_torch_custom_ops_are_registered(svb, net):
     """The C ABI is reachable as torch.ops.svb200.* (schema, CUDA kernel, fake kernel, autograd): direct calls and
     torch.library.opcheck on the differentiable entry points."""
