@@ -302,11 +302,19 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world, n_ext
         L.svb_gemm_bf16_2cta(PA, PB, 1, ptr(Cg), None, Mg, Ng, Kg, ctypes.c_int64(Kg), ctypes.c_int64(Kg),
                              ctypes.c_int64(Ng), 0, stream_ptr())
 
-    ms = dev_time(input_gemm, 10, 3)
+    def input_gemm_persistent():
+        L.svb_gemm_persistent(ptr(Ag), ptr(Bg), ptr(Cg), None, Mg, Ng, Kg, ctypes.c_int64(Kg), ctypes.c_int64(Kg),
+                              ctypes.c_int64(Ng), 0, stream_ptr())
+
+    ms = dev_time(input_gemm_persistent, 10, 3)
+    ms_tile = dev_time(input_gemm, 10, 3)
     tf = 2.0 * Mg * Ng * Kg / (ms * 1e-3) / 1e12
     out["lstm_input_gemm_standalone"] = {"M": Mg, "N": Ng, "K": Kg, "ms": ms, "tflops": tf,
                                          "frac_of_sustained_bf16_peak": tf / peaks()[0].get("bf16_tflops_sustained", 1400.0),
-                                         "kernel": "tc_gemm_kernel<256,6,K-major,pair> (cta_group::2, 256x256 pair tiles)"}
+                                         "kernel": "pgemm_kernel (persistent CTA pairs, cta_group::2 256x256 tiles, two TMEM "
+                                                   "accumulators: epilogue of tile i under the MMAs of tile i+1)",
+                                         "one_tile_per_cta_pair_kernel_ms": ms_tile,
+                                         "one_tile_per_cta_pair_tflops": 2.0 * Mg * Ng * Kg / (ms_tile * 1e-3) / 1e12}
     del Ag, Bg, Cg
 
     # ---- EER sweep at N=1024, M=6 (3 enrollment + 3 verification)

@@ -37,6 +37,14 @@ int svb_gemm_bf16(const void* const* A, const void* const* B, int nterms, float*
 int svb_gemm_bf16_2cta(const void* const* A, const void* const* B, int nterms, float* C, const float* bias, int M,
                        int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int mn, void* stream);
 
+/* Persistent CTA-pair kernel for short reductions (the LSTM input projection W_ih x_t over all frames taken as one
+ * batched GEMM, speech_embedder_net.py:19,28: [T*B x 768] . [768 x 3072] at BASELINE configs[1]): C[M,N] (fp32, pitch
+ * ldc) = A[M,K] . B[N,K]^T + bias[n].  Operands K-major with 2-byte elements (f16 != 0: IEEE half, else bf16);
+ * K % 64 == 0, N % 256 == 0.  74 CTA pairs walk the 256 x 256 tiles; two TMEM accumulators overlap each tile's
+ * epilogue with the next tile's MMAs (csrc/pgemm.cu). */
+int svb_gemm_persistent(const void* A, const void* B, float* C, const float* bias, int M, int N, int K, int64_t lda,
+                        int64_t ldb, int64_t ldc, int f16, void* stream);
+
 /* ---- SpeechEmbedder (speech_embedder_net.py:15-33): 3-layer LSTM + last-frame Linear + L2 norm ------------------
  * Dimensions: B utterances, T frames, I mel bins, H hidden (multiple of 128), L layers (<= 8), P projection size. */
 

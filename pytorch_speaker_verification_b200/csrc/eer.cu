@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
   __shared__ int hist[kSweepWarps][kBk / 2][32];
   __shared__ int wsum[kSweepWarps][kBk];
   __shared__ int h_diag[kBk];
+  __shared__ int suf_all[kBk], suf_diag[kBk];   // suffix sums of the buckets
   __shared__ float far_s[kMaxThr], frr_s[kMaxThr];
   __shared__ int last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,12 +212,26 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
     wsum[warp][bk] = tot;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {       // count(sim > thr[t]) = sum_{bk > t} hist[bk]
-    int sa = 0, sd = 0;
-    for (int bk = t + 1; bk <= T; ++bk) {
-      sa += wsum[0][bk] + wsum[1][bk] + wsum[2][bk] + wsum[3][bk];
-      sd += h_diag[bk];
+  // count(sim > thr[t]) = sum_{bk > t} hist[bk]: suffix sums of the 64 buckets by warp shuffles (warp 0: all elements,
+  // warp 1: the diagonal) -- the per-threshold loops over the buckets were the longest part of a CTA's chain
+  if (warp < 2) {
+    int lo = warp == 0 ? wsum[0][lane] + wsum[1][lane] + wsum[2][lane] + wsum[3][lane] : h_diag[lane];
+    int hi = warp == 0 ? wsum[0][32 + lane] + wsum[1][32 + lane] + wsum[2][32 + lane] + wsum[3][32 + lane] : h_diag[32 + lane];
+    if (lane > T) lo = 0;
+    if (32 + lane > T) hi = 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int yl = __shfl_down_sync(0xffffffffu, lo, o), yh = __shfl_down_sync(0xffffffffu, hi, o);
+      if (lane + o < 32) { lo += yl; hi += yh; }
     }
+    lo += __shfl_sync(0xffffffffu, hi, 0);
+    int* suf = warp == 0 ? suf_all : suf_diag;
+    suf[lane] = lo; suf[32 + lane] = hi;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int sa = t + 1 < kBk ? suf_all[t + 1] : 0;
+    const int sd = t + 1 < kBk ? suf_diag[t + 1] : 0;
     cnt_all[(size_t)i * T + t] = sa;
     cnt_diag[(size_t)i * T + t] = sd;
     unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x & 7) * 2 * T;
