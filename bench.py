@@ -525,9 +525,18 @@ def main():
         from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
         reducer = OverlappedGradReducer()
 
-    def fwd_bwd(x):
+    loss_events = []                        # (start, end) CUDA events around the loss forward, filled while profiling
+
+    def fwd_bwd(x, profile=False):
         emb = net(x)
-        loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
+        if profile:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
+            ev[1].record()
+            loss_events.append(ev)
+        else:
+            loss = loss_mod(emb.reshape(N_SPK, M_UTT, PROJ))
         if reducer is not None:               # bucketed all-reduce started from inside backward
             with reducer:
                 loss.backward()
@@ -584,10 +593,10 @@ def main():
         L.svb_profile_enable(0)
         return {n: acc[i] / steps for i, n in enumerate(PHASES)}
 
-    def value_step():
+    def value_step(profile=False):
         for p in list(params) + [crit.w, crit.b]:
             p.grad = None
-        return fwd_bwd(x_dev)
+        return fwd_bwd(x_dev, profile)
 
     def dist_check():
         """N ranks == 1 rank: the sharded step (speakers split over the ranks, d-vector all-gather, global GE2E, SUM
@@ -642,7 +651,10 @@ def main():
 
     ms_e2e_fused = timed(full_step_fused, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    phases = phase_profile(value_step)          # every rank: the step contains collectives
+    phases = phase_profile(lambda: value_step(True))          # every rank: the step contains collectives
+    # GE2E forward+gradients as the step runs it: one fused launch on one GPU; at N > 1 the centroid all-gather, this
+    # rank's rows against all centroids, the all-reduce of [dC | loss, dw, db] and the waits for the slowest rank
+    phases["ge2e_loss_incl_collectives"] = sum(a.elapsed_time(b) for a, b in loss_events) / max(1, len(loss_events))
     barrier()
     loss_val = float(loss_host)
     check = dist_check() if world > 1 else None

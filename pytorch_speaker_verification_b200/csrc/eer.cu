@@ -189,15 +189,16 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
         const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+          // bucket 0 (not above the first threshold: almost every different-speaker similarity) enters no count
           const int bk = bucket_of64(vv[e], thr);
-          atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
+          if (bk) atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
         }
       }
     }
   } else {
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
       const int bk = bucket_of64(base[idx], thr);
-      atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
+      if (bk) atomicAdd(&h[bk >> 1][lane], 1 << ((bk & 1) * 16));
     }
   }
   for (int m = threadIdx.x; m < Mv; m += blockDim.x) {      // the diagonal column of this speaker's row block

@@ -31,8 +31,13 @@ constexpr int kWlTile = 64;            // batch rows per tile (= MMA N)
 // 64-wide K blocks per ring stage.  An mbarrier try_wait costs ~170 cycles even when the phase is already complete
 // (scripts/ubench/mma_issue.cu) and the tensor pipe drains meanwhile (tcgen05.mma issue behaves like a depth-1
 // queue), so waits must be rare: 6 K blocks = 24 MMAs of N = 64 (768 cycles of tensor work) per wait.
+#ifdef SVB_WL_RING_ALT                 // experiment (make ALT=1): finer stages, same bytes
+constexpr int kWlKbPerStage = 3;
+constexpr int kWlStages = 6;
+#else
 constexpr int kWlKbPerStage = 6;
 constexpr int kWlStages = 3;           // operand ring: 3 x 6 x [64 rows x 64 K] fp16 = 144 KB (1.5 tiles in flight)
+#endif
 constexpr int kWlKbBytes = kWlTile * 128;
 constexpr int kWlStageBytes = kWlKbPerStage * kWlKbBytes;
 constexpr int kWlGinRing = 3;          // frames of gin kept in flight per layer

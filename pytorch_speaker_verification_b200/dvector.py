@@ -113,6 +113,37 @@ def _chunk_plan(Ts):
     return W, starts, np.concatenate(seg).astype(np.int32), counts
 
 
+_stage_workers = None
+
+
+def _workers():
+    global _stage_workers
+    if _stage_workers is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _stage_workers = ThreadPoolExecutor(max_workers=4, thread_name_prefix="svb-stage")
+    return _stage_workers
+
+
+def _fill_specs(dst, specs):
+    """dst (nmels, F) float32 view of a pinned buffer <- the utterances' log-mels side by side.  600 MB of host
+    copies for 12.5 k utterances: split over the staging workers (numpy copies release the GIL)."""
+    n = len(specs)
+    if n < 64:
+        np.concatenate([np.asarray(s, dtype=np.float32) for s in specs], axis=1, out=dst)
+        return
+    offs = np.concatenate([[0], np.cumsum([int(s.shape[1]) for s in specs])])
+    parts = 4
+    bounds = [n * i // parts for i in range(parts + 1)]
+
+    def job(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi > lo:
+            np.concatenate([np.asarray(s, dtype=np.float32) for s in specs[lo:hi]], axis=1,
+                           out=dst[:, int(offs[lo]):int(offs[hi])])
+
+    list(_workers().map(job, range(parts)))
+
+
 @torch.no_grad()
 def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 16):
     """Batched extraction for many utterances: specs = list of (nmels, T_u) log-mel arrays.
@@ -120,8 +151,11 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
 
     The utterances are processed in chunks of about ``chunk_frames`` frames: per chunk one pinned staging copy, one
     asynchronous H2D copy, one window-gather launch, the LSTM on <= max_windows windows at a time, one segment-mean
-    launch and an asynchronous D2H copy into pinned memory.  Nothing synchronises until the last chunk is queued, so
-    the host-side staging and index math of chunk i+1 overlap the GPU work of chunk i."""
+    launch and an asynchronous D2H copy into pinned memory.  The staging of the chunks (index math + the host copies
+    into page-locked memory, the largest host cost) runs on a producer thread up to three chunks ahead of the thread
+    that queues the GPU work; nothing synchronises until the last chunk is queued."""
+    import queue
+    import threading
     dev = ops._target_device(*embedder_net.parameters())        # the module's device, else the current one
     D = embedder_net.projection.out_features
     n = len(specs)
@@ -142,6 +176,15 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
     pending = []          # per chunk: (pinned result view, D2H event, buffers) until harvested
     counts_of = {}
     res_chunks = [None] * (len(bounds) - 1)
+    pool_lock = threading.Lock()
+
+    def take(nbytes):
+        with pool_lock:
+            return _pool.take(nbytes)
+
+    def give(t):
+        with pool_lock:
+            _pool.give(t)
 
     def harvest(block):
         """Copy finished chunks out of their page-locked buffers (one memcpy per chunk) and recycle the buffers;
@@ -157,26 +200,44 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
                     ev.synchronize()
                 res_chunks[k] = np.array(hv.numpy())
                 for t in bufs:
-                    _pool.give(t)
+                    give(t)
             pending[k] = None
 
+    staged = queue.Queue(maxsize=3)
+
+    def producer():
+        try:
+            for k, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+                Ts = Ts_all[lo:hi]
+                F = int(Ts.sum())
+                W, starts, seg, counts = _chunk_plan(Ts)
+                if W == 0:
+                    staged.put((k, None, counts, 0, 0, 0, 0))
+                    continue
+                # one staging buffer: [log-mel (nmels, F) float32 | starts int32 | seg int32]
+                nb_spec, nb_st, nb_seg = nmels * F * 4, starts.size * 4, seg.size * 4
+                stage = take(nb_spec + nb_st + nb_seg)
+                sv = stage.numpy()
+                _fill_specs(sv[:nb_spec].view(np.float32).reshape(nmels, F), specs[lo:hi])
+                sv[nb_spec:nb_spec + nb_st].view(np.int32)[:] = starts
+                sv[nb_spec + nb_st:nb_spec + nb_st + nb_seg].view(np.int32)[:] = seg
+                staged.put((k, stage, counts, W, (nb_spec, nb_st, nb_seg), F, int(seg.size) - 1))
+        except BaseException as exc:                    # surfaced on the consumer side
+            staged.put(exc)
+
+    th = threading.Thread(target=producer, name="svb-extract-stage", daemon=True)
+    th.start()
     with torch.cuda.device(dev):
-        for k, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
-            Ts = Ts_all[lo:hi]
-            F = int(Ts.sum())
-            W, starts, seg, counts = _chunk_plan(Ts)
+        for _ in range(len(bounds) - 1):
+            item = staged.get()
+            if isinstance(item, BaseException):
+                raise item
+            k, stage, counts, W, sizes, F, P = item
             res_chunks[k] = counts                       # replaced by the data in harvest() when the chunk has windows
-            if W == 0:
+            if stage is None:
                 pending.append((None, None, ()))
                 continue
-            # one staging buffer: [log-mel (nmels, F) float32 | starts int32 | seg int32]
-            nb_spec, nb_st, nb_seg = nmels * F * 4, starts.size * 4, seg.size * 4
-            stage = _pool.take(nb_spec + nb_st + nb_seg)
-            sv = stage.numpy()
-            np.concatenate([np.asarray(s, dtype=np.float32) for s in specs[lo:hi]], axis=1,
-                           out=sv[:nb_spec].view(np.float32).reshape(nmels, F))
-            sv[nb_spec:nb_spec + nb_st].view(np.int32)[:] = starts
-            sv[nb_spec + nb_st:nb_spec + nb_st + nb_seg].view(np.int32)[:] = seg
+            nb_spec, nb_st, nb_seg = sizes
             g = stage[:nb_spec + nb_st + nb_seg].to(dev, non_blocking=True)
             cat = g[:nb_spec].view(torch.float32).view(nmels, F)
             st_d = g[nb_spec:nb_spec + nb_st].view(torch.int32)
@@ -187,8 +248,7 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
             else:
                 emb = torch.cat([embedder_net(frames[i:i + max_windows]) for i in range(0, W, max_windows)], dim=0)
             out = ops.segment_mean(emb, seg_d)                             # (P, D) float64
-            P = int(out.shape[0])
-            host = _pool.take(P * D * 8)
+            host = take(P * D * 8)
             hv = host[:P * D * 8].view(torch.float64).view(P, D)
             hv.copy_(out, non_blocking=True)
             ev = torch.cuda.Event()
@@ -197,6 +257,7 @@ def extract_dvectors(embedder_net, specs, max_windows=65536, chunk_frames=1 << 1
             counts_of[k] = counts
             harvest(False)
         harvest(True)
+    th.join()
     res = []
     for k in range(len(res_chunks)):
         counts = counts_of.get(k)
