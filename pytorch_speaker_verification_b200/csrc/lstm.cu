@@ -558,34 +558,38 @@ __global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restri
 // model's gradients (loss ~ 0.4, |dL/dh| ~ 1e-5) would sit in the fp16 subnormals, a SUM loss over thousands of rows
 // grows the other way.  Under the scale every backward sees max |dL/dh_last| in [1, 2), so the result is the same
 // function of the gradient's DIRECTION whatever its magnitude; the kernels that finish a parameter gradient multiply
-// by 1/s (`inv`, exact: powers of two).  One block: 2 passes over B x H floats that the projection backward just wrote.
-__global__ void __launch_bounds__(1024) grad_scale_kernel(float* __restrict__ dh, size_t n, float* __restrict__ gscale) {
-  __shared__ float red[32];
-  __shared__ float s_sh;
+// by 1/s (`inv`, exact: powers of two).
+// Two launches over the B x H floats the projection backward just wrote (L2-resident): block maxima -> atomicMax on the
+// bit pattern (non-negative floats order like unsigned integers) into gscale[2] (zeroed by the caller), then every
+// block derives the scale from it and scales its part; block 0 records {s, 1/s}.  (One 1024-thread block doing both
+// passes took 76 us per step.)
+__global__ void __launch_bounds__(256) grad_amax_kernel(const float* __restrict__ dh, size_t n, float* __restrict__ gscale) {
+  __shared__ float red[8];
   float m = 0.f;
-  for (size_t i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(dh[i]));
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) m = fmaxf(m, fabsf(dh[i]));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = red[threadIdx.x];
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) {
-      float sc = 1.f;
-      if (m > 0.f && m < 3.0e38f) {            // (zero, inf or NaN gradients: unscaled)
-        int e = ilogbf(m);
-        e = e < -100 ? -100 : e > 100 ? 100 : e;
-        sc = ldexpf(1.f, -e);
-      }
-      s_sh = sc;
-      gscale[0] = sc;
-      gscale[1] = 1.f / sc;
-    }
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    // NaN compares false in fmaxf and is dropped; +inf passes through and disables the scale below
+    atomicMax(reinterpret_cast<unsigned*>(gscale + 2), __float_as_uint(m));
   }
-  __syncthreads();
-  const float sc = s_sh;
+}
+__global__ void __launch_bounds__(256) grad_scale_kernel(float* __restrict__ dh, size_t n, float* __restrict__ gscale) {
+  const float m = __uint_as_float(*reinterpret_cast<const volatile unsigned*>(gscale + 2));
+  float sc = 1.f;
+  if (m > 0.f && m < 3.0e38f) {              // (zero, inf or NaN gradients: unscaled)
+    int e = ilogbf(m);
+    e = e < -100 ? -100 : e > 100 ? 100 : e;
+    sc = ldexpf(1.f, -e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    gscale[0] = sc;
+    gscale[1] = 1.f / sc;
+  }
   if (sc != 1.f)
-    for (size_t i = threadIdx.x; i < n; i += 1024) dh[i] *= sc;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dh[i] *= sc;
 }
 __global__ void scale_inplace_kernel(float4* __restrict__ x, size_t n4, const float* __restrict__ inv) {
   const float k = __ldg(inv);
@@ -968,7 +972,9 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
   }
   colsum_rows_kernel<<<(P + 31) / 32, dim3(32, 32), 0, s>>>(w.dy, grads[4 * L + 1], B, P);
   sgemm64(w.dy, P, 1, proj_w, 1, H, w.dh_last, H, B, H, P, 1, s);       // dh_last[B,H] = dy W_proj
-  grad_scale_kernel<<<1, 1024, 0, s>>>(w.dh_last, BH, w.gscale);       // BPTT runs on dh_last * 2^k, max in [1, 2)
+  cudaMemsetAsync(w.gscale + 2, 0, 4, s);
+  grad_amax_kernel<<<148, 256, 0, s>>>(w.dh_last, BH, w.gscale);
+  grad_scale_kernel<<<148, 256, 0, s>>>(w.dh_last, BH, w.gscale);      // BPTT runs on dh_last * 2^k, max in [1, 2)
   const float* inv_scale = w.gscale + 1;
   auto unscale = [&](float* g, size_t n) {                             // gradients stored directly by a GEMM epilogue
     scale_inplace_kernel<<<148 * 2, 256, 0, s>>>(reinterpret_cast<float4*>(g), n / 4, inv_scale);
