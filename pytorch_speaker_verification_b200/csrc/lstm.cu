@@ -1024,6 +1024,9 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     }
     bp.dcnt = w.dcnt; bp.xcnt = w.xcnt; bp.dh_last = w.dh_last; bp.inv_scale = inv_scale;
     bp.trace = reinterpret_cast<long long*>(g_trace_bwd);
+    bp.ablate = g_ablate;
+    bp.trace_u = getenv("SVB_TRACE_U") ? atoi(getenv("SVB_TRACE_U")) : 0;
+    bp.trace_s = getenv("SVB_TRACE_S") ? atoi(getenv("SVB_TRACE_S")) : 0;
     bp.trace_l = getenv("SVB_TRACE_LAYER") ? atoi(getenv("SVB_TRACE_LAYER")) : 1;
     bp.B = B; bp.T = T; bp.L = L; bp.H = H; bp.nt = nt;
     cudaMemsetAsync(w.dcnt, 0, w.bcnt_bytes, s);

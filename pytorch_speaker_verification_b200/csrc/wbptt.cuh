@@ -28,38 +28,42 @@
 
 constexpr int kWbTile = 64;
 constexpr int kWbKb = 12;              // 64-wide K blocks per CTA (K slice of 768)
-#ifdef SVB_WB_RING_ALT                 // experiment (make ALT=1 -> libsvb200_alt.so): finer, deeper operand ring
-constexpr int kWbKbPerStage = 2;       // 8 MMAs per barrier wait
-constexpr int kWbStages = 5;           // ring: 5 x 16 KB (a tile is 6 stages)
-#else
 constexpr int kWbKbPerStage = 3;       // 12 MMAs per barrier wait
-constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages)
-#endif
+constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages; 5 x 16 KB measured 5 % slower)
 constexpr int kWbStageBytes = kWbKbPerStage * kWbTile * 128;
 constexpr int kWbXRing = 3;
-#ifdef SVB_DEPS_ALT
-constexpr int kWbDeps = 8;
-#else
-constexpr int kWbDeps = 4;
-#endif
-constexpr int kWbEpiWarps = 16;
-constexpr int kWbThreads = 32 * kWbEpiWarps + 128;
-constexpr int kWbWarpTma = kWbEpiWarps, kWbWarpMma = kWbEpiWarps + 1, kWbWarpStore = kWbEpiWarps + 2,
-              kWbWarpPoll = kWbEpiWarps + 3;   // lane 0: dependency poller, lane 1: epilogue-input loader
+constexpr int kWbDeps = 8;             // dependency slots: the poller runs up to 8 tiles ahead of the slowest waiter
+// Warp roles.  Every single-thread role has a warp of its own: two roles in one warp run time-sliced, and a lane that
+// sleeps in mbarrier.try_wait holds the other one up (poller and input loader shared a warp at first: the TMA producer
+// then waited 1200 cycles per tile for dependencies that had been satisfied long before).  The single-thread roles sit
+// in the highest warp ids (the sub-partition arbiter prefers the highest eligible warp).
+constexpr int kWbMathWarps = 16;       // warps 0-15: split-K reduction + gate backward, thread = (row, 4 units)
+constexpr int kWbMathThreads = 32 * kWbMathWarps;
+constexpr int kWbWarpXch = kWbMathWarps;   // 4 exchange warps (TMEM lane quarter = warp & 3): accumulator -> staged quarters
+constexpr int kWbWarpLoad = kWbWarpXch + 4, kWbWarpPoll = kWbWarpXch + 5, kWbWarpStore = kWbWarpXch + 6,
+              kWbWarpTma = kWbWarpXch + 7, kWbWarpMma = kWbWarpXch + 8;
+constexpr int kWbThreads = 32 * (kWbWarpMma + 1);     // 25 warps = 800 threads, 72 registers
+static_assert(kWbWarpXch % 4 == 0, "exchange warp w must own TMEM lane quarter w & 3");
 constexpr int kWbAccCol = 384;
-// epilogue tiles (in place): gates / dG 2 x 8 KB boxes, c_t, c_{t-1}, dc
-// Three in-place buffers (gates -> dG 2 x 8 KB boxes, dc) + two read-only buffers (c_t, c_{t-1}): the in-place tiles
-// are busy from their TMA load through the gate math until their TMA store has drained (load latency + math + store
-// ~ 5000 cycles), which with two buffers alone bounded the tile period.
+// epilogue tiles.  Three in-place buffers (gates -> dG 2 x 8 KB boxes, running dL/dc): busy from their TMA load through
+// the gate math until their TMA store has drained (load latency + math + store ~ 5000 cycles; two buffers bounded the
+// tile period).  Two read-only buffers for c_{t-1}.  c_t itself is NOT loaded: tanh(c_t) is recomputed from
+// c_t = f c_{t-1} + i g with the stashed activations (no measurable effect on the gradients,
+// scripts/precision_study_bwd.py "c_t recomputed"; one 8 KB TMA load per tile and 16 KB of shared memory less).
 constexpr int kWbIo = 3;
 constexpr int kWbOffG = 0, kWbOffDc = 16384, kWbIoBytes = 24576;       // per in-place buffer
-constexpr int kWbOffCt = 0, kWbOffCp = 8192, kWbCBytes = 16384;        // per read-only buffer
-constexpr int kWbStgBytes = 3 * kWbIoBytes + 2 * kWbCBytes;            // 104 KB
-// three peers' partial quarters, fp16: [slot][8-row group 8][lane 32] x 8 halves (16 B).  fp16 (2^-11) halves the DSMEM
-// traffic, which bounds the kernel; the partial sums are O(|dh|) and far from the fp16 range limits.
-constexpr int kWbRecvBytes = 3 * 4096;
-constexpr int kWbDhBytes = 8192;        // reduced dh tile [64 rows][32 units] fp32
-constexpr int kWbSmem = kWbStages * kWbStageBytes + kWbStgBytes + 2 * kWbRecvBytes + 2 * kWbDhBytes + 1024 + 1024;
+constexpr int kWbCpBytes = 8192;                                       // per c_{t-1} buffer
+constexpr int kWbStgBytes = kWbIo * kWbIoBytes + 2 * kWbCpBytes;       // 88 KB
+// Split-K exchange.  A partial quarter is staged as fp16 [64 rows][32 units] (4 KB; fp16 = 2^-11 halves the DSMEM
+// traffic, the partial sums are O(|dh|) under the gradient scale) and leaves through ONE bulk copy per destination
+// (cp.async.bulk.shared::cluster, complete_tx on the receiver's mbarrier): 730 cycles per 3 x 4 KB round against
+// 1480 for per-thread st.shared::cluster stores + release arrives (scripts/ubench/dsmem_push.cu), and no warp waits
+// for a remote round trip.  The own quarter stays fp32 [64 rows][32 units].
+constexpr int kWbQuarterBytes = kWbTile * 32 * 2;
+constexpr int kWbRecvBytes = 3 * kWbQuarterBytes;
+constexpr int kWbSendBytes = 3 * kWbQuarterBytes;
+constexpr int kWbOwnBytes = kWbTile * 32 * 4;
+constexpr int kWbSmem = kWbStages * kWbStageBytes + kWbStgBytes + 2 * kWbRecvBytes + 2 * kWbSendBytes + 2 * kWbOwnBytes + 1024 + 1024;
 static_assert(kWbSmem <= 227 * 1024, "shared memory budget of the BPTT kernel");
 
 struct __align__(64) WbLayer {
@@ -68,7 +72,7 @@ struct __align__(64) WbLayer {
   CUtensorMap t_dc;        // fp32 running dL/dc [1][B][H], box {32, 64} SW128, load + store
   const __nv_bfloat16* whhT;   // [H][4H]
   const __nv_bfloat16* wihT;   // [H][4H] (layers >= 1)
-  float* xring;            // dX produced by X(l): [kWbXRing][nt][H/32][64 x 32] fp32, fragment order (layers >= 1)
+  float* xring;            // dX produced by X(l): [kWbXRing][nt][H/32][64 rows x 32 units] fp32 (layers >= 1)
   float* gbias_ih;         // bias gradients of the layer (reference row order), written at the end of the kernel
   float* gbias_hh;         // b_ih and b_hh enter the pre-activation as a sum: identical gradients
 };
@@ -79,6 +83,8 @@ struct __align__(64) WbParams {
   const float* dh_last;    // [B][H] dL/dh of the top layer's last frame (times the gradient scale, lstm.cu)
   const float* inv_scale;  // device scalar: 1 / gradient scale, applied to the bias gradients on the way out
   long long* trace;
+  int ablate;              // debug (SVB_WB_ACCOUNT builds only): parts switched off for timing experiments, results are garbage
+  int trace_u, trace_s;    // debug: unit tile (cluster) and cluster rank of the traced CTAs (env SVB_TRACE_U / SVB_TRACE_S, default 0)
   int trace_l;             // debug: layer whose R(l, 0, 0) / X(l, 0, 0) CTAs are traced (env SVB_TRACE_LAYER, default 1)
   int B, T, L, H, nt;
 };
@@ -87,7 +93,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t
   const uint32_t addr = map_to_cta(smem_u32(local_bar), cta);
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-// relaxed variant: signals "I have consumed your data" (the loads it orders have already returned their values)
+// relaxed variant: signals "I have consumed your data" (the loads it orders have already returned their values; a
+// release here costs the signalling warp a cluster-scope fence per tile)
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* local_bar, uint32_t cta) {
   const uint32_t addr = map_to_cta(smem_u32(local_bar), cta);
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
@@ -113,9 +120,44 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
-__device__ __forceinline__ void st_cluster_u4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+// shared memory of this CTA -> shared memory of a peer CTA; the bytes are credited to the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_push(uint32_t dst_cluster_addr, uint32_t src_addr, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(src_addr), "r"(bytes), "r"(bar_cluster_addr) : "memory");
 }
+// Warp-wide wait; experiment: ONE polling lane + __syncwarp
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#ifdef SVB_WB_ONE_LANE_WAIT   // measured: 4.3-5.0 ms against 4.05 ms with every lane polling (the elected lane + __syncwarp adds latency)
+  if (lane_id() == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t parity) {
+#ifdef SVB_WB_ONE_LANE_WAIT   // measured: 4.3-5.0 ms against 4.05 ms with every lane polling (the elected lane + __syncwarp adds latency)
+  if (lane_id() == 0) mbar_wait_cluster(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait_cluster(bar, parity);
+#endif
+}
+__device__ __forceinline__ void math_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * 16) : "memory"); }
+
+// wait accounting (debug; make ALT=1 ALTFLAGS=-DSVB_WB_ACCOUNT, scripts/account_wbptt.py): cycles every role thread spends
+// in each of its waits, summed over the kernel, per CTA: trace[2 nt 16 + 256 + 32 cta + slot]
+#ifdef SVB_WB_ACCOUNT
+#define WB_ACC(k, ...) do { const long long a0_ = clock64(); __VA_ARGS__; wacc[k] += clock64() - a0_; } while (0)
+#define WB_ACC_OUT(slot0, n) do { if (p.trace) for (int k_ = 0; k_ < (n); ++k_) p.trace[2 * nt * 16 + 256 + 32 * blockIdx.x + (slot0) + k_] = wacc[k_]; } while (0)
+// ablation mask (scripts/ablate_wbptt.py): 1 MMAs, 2 gate math, 4 operand loads, 8 dependencies, 16 exchange staging
+// stores, 32 epilogue input loads, 64 DSMEM push, 128 dG / dc stores, 256 the math warps' proxy fence
+#define WB_ABL(bit) ((p.ablate & (bit)) != 0)
+#else
+#define WB_ABL(bit) false
+#define WB_ACC(k, ...) do { __VA_ARGS__; } while (0)
+#define WB_ACC_OUT(slot0, n) do { } while (0)
+#endif
+
 template <int H>
 __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_constant__ WbParams p) {
   constexpr int NS = H / 32;                 // 32-unit slices per layer (= R CTAs per layer)
@@ -125,25 +167,26 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint8_t* stg = ring + kWbStages * kWbStageBytes;
-  uint8_t* cst = stg + 3 * kWbIoBytes;         // the two c buffers
+  uint8_t* cst = stg + kWbIo * kWbIoBytes;     // the two c_{t-1} buffers
   uint8_t* recv = stg + kWbStgBytes;
-  uint8_t* dhb = recv + 2 * kWbRecvBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(dhb + 2 * kWbDhBytes);
+  uint8_t* send = recv + 2 * kWbRecvBytes;
+  uint8_t* own = send + 2 * kWbSendBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(own + 2 * kWbOwnBytes);
   uint64_t* empty = full + kWbStages;
   uint64_t* acc_full = empty + kWbStages;      // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2] 16 warps
+  uint64_t* acc_empty = acc_full + 2;          // [2] 4 exchange warps
   uint64_t* in_full = acc_empty + 2;           // [3] epilogue input tiles landed (tx)
-  uint64_t* stg_full = in_full + 3;            // [3] 256 math threads: outputs staged (and c tiles read)
+  uint64_t* stg_full = in_full + 3;            // [3] 16 math warps: outputs staged (and c tiles read)
   uint64_t* stg_free = stg_full + 3;           // [3] store thread: in-place buffer reusable
-  uint64_t* recv_full = stg_free + 3;          // [2] 6 remote warps: partial quarters of the three peers landed
-  uint64_t* peer_free = recv_full + 2;         // [2] 12 remote warps: my three receivers consumed tile it-2
-  uint64_t* dep_ready = peer_free + 2;         // [kWbDeps]
+  uint64_t* recv_full = stg_free + 3;          // [2] 1 arming arrive + 12 KB of transactions: the peers' quarters landed
+  uint64_t* peer_free = recv_full + 2;         // [2] 3 remote arrives: my three receivers consumed (and re-armed) use k-1
+  uint64_t* send_ready = peer_free + 2;        // [2] the owner exchange warp: own quarter staged
+  uint64_t* consumed = send_ready + 2;         // [2] math thread 0: recv + own of this use are in registers
+  uint64_t* dep_ready = consumed + 2;          // [kWbDeps]
   uint64_t* dep_free = dep_ready + kWbDeps;    // [kWbDeps]
-  uint64_t* x_done = dep_free + kWbDeps;       // [2] X: owner threads wrote the dX tile
+  uint64_t* x_done = dep_free + kWbDeps;       // [2] X: 16 math warps wrote the dX tile
   uint64_t* x_taken = x_done + 2;              // [2]
-  uint64_t* dh_full = x_taken + 2;             // [2] 64 owner threads: reduced dh tile written
-  uint64_t* dh_free = dh_full + 2;             // [2] 256 math threads: dh tile consumed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dh_free + 2);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(x_taken + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cl = blockIdx.x >> 2;
@@ -156,37 +199,44 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   const int nt = p.nt, T = p.T;
   const long long total = (long long)T * nt;
   const bool has_x = is_R && l + 1 < p.L;      // dX from the layer above arrives through its ring
-  // debug trace: R(1, 0, 0) rows [0, nt), X(1, 0, 0) rows [nt, 2 nt): 16 clock64 stamps per tile of frame T/2
-  long long* const trace_cta = (p.trace && l == p.trace_l && u == 0 && s == 0) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
+  // debug trace: R(l, 0, 0) rows [0, nt), X(l, 0, 0) rows [nt, 2 nt): 16 clock64 stamps per tile of frame T/2
+  long long* const trace_cta = (p.trace && l == p.trace_l && u == p.trace_u && s == p.trace_s) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
   const long long t_cta0 = clock64();
+#ifdef SVB_WB_ACCOUNT
+  long long wacc[6] = {0, 0, 0, 0, 0, 0};
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWbStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 8);               // the eight exchange warps
-      mbar_init(&recv_full[b], 6);               // 3 senders x 2 warps
-      mbar_init(&peer_free[b], 6);               // 3 receivers x 2 owner warps
-      mbar_init(&x_done[b], 64);
+      mbar_init(&acc_empty[b], 4);
+      mbar_init(&recv_full[b], 1);
+      mbar_init(&peer_free[b], 3);
+      mbar_init(&send_ready[b], 1);
+      mbar_init(&consumed[b], 1);
+      mbar_init(&x_done[b], kWbMathWarps);
       mbar_init(&x_taken[b], 1);
-      mbar_init(&dh_full[b], 64);
-      mbar_init(&dh_free[b], 256);
     }
     for (int b = 0; b < 3; ++b) {
       mbar_init(&in_full[b], 1);
-      mbar_init(&stg_full[b], 256);              // the eight math warps
+      mbar_init(&stg_full[b], kWbMathWarps);       // one arrive per warp: N arrivals on one mbarrier serialise
       mbar_init(&stg_free[b], 1);
     }
     for (int d = 0; d < kWbDeps; ++d) {
       mbar_init(&dep_ready[d], 1);
-      mbar_init(&dep_free[d], is_R ? 2 + 2 : 1);     // producer (+ input loader + the two owner warps of R)
+      mbar_init(&dep_free[d], is_R ? (has_x ? 2 + kWbMathWarps : 2) : 1);   // producer (+ input loader (+ the math warps) of R)
     }
     fence_mbar_init();
+    // the first use of both receive buffers is armed here; later uses are armed by math thread 0 BEFORE it tells the
+    // senders that the buffer is free, so a complete_tx can never precede its expect_tx
+    mbar_expect_tx(&recv_full[0], kWbRecvBytes);
+    mbar_expect_tx(&recv_full[1], kWbRecvBytes);
     tma_prefetch_desc(&ly.t_dg);
   }
   if (warp == kWbWarpMma) tmem_alloc<512>(tmem_holder);
   tc_fence_before();
-  cluster_sync_all();                          // every CTA's barriers are initialised before any remote arrive
+  cluster_sync_all();                          // every CTA's barriers are initialised before any remote arrive / push
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
 
@@ -216,42 +266,44 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     for (int t = T - 1; t >= 0; --t) {
       for (int j = 0; j < nt; ++j, ++it) {
         const int d = (int)(it % kWbDeps);
-        mbar_wait(&dep_free[d], (uint32_t)(((it / kWbDeps) & 1) ^ 1));
-        if (is_R) {
-          wait_two_counters(t < T - 1 ? p.dcnt + l * nt + j : nullptr, (unsigned)(NS * (T - 1 - t)),
-                            has_x ? p.xcnt + ((size_t)(l + 1) * NS + ns) * nt + j : nullptr, (unsigned)(T - t));
+        WB_ACC(0, mbar_wait(&dep_free[d], (uint32_t)(((it / kWbDeps) & 1) ^ 1)));
+        if (WB_ABL(8)) {
+        } else if (is_R) {
+          WB_ACC(1, wait_two_counters(t < T - 1 ? p.dcnt + l * nt + j : nullptr, (unsigned)(NS * (T - 1 - t)),
+                            has_x ? p.xcnt + ((size_t)(l + 1) * NS + ns) * nt + j : nullptr, (unsigned)(T - t)));
         } else {
-          wait_two_counters(p.dcnt + l * nt + j, (unsigned)(NS * (T - t)),
-                            T - t > kWbXRing ? p.dcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (T - t - kWbXRing)));
+          WB_ACC(1, wait_two_counters(p.dcnt + l * nt + j, (unsigned)(NS * (T - t)),
+                            T - t > kWbXRing ? p.dcnt + (l - 1) * nt + j : nullptr, (unsigned)(NS * (T - t - kWbXRing))));
         }
         mbar_arrive(&dep_ready[d]);
       }
     }
-  } else if (warp == kWbWarpPoll && lane == 1) {
+    WB_ACC_OUT(0, 2);
+  } else if (warp == kWbWarpLoad && lane == 0) {
     // ------------------------------------------------------------------ epilogue-input loader (R only)
     if (is_R) {
       long long it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int buf = (int)(it & 1);
-          const uint32_t upar = (uint32_t)((it >> 1) & 1);
           const int d = (int)(it % kWbDeps);
-          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));   // our own dc store of frame t+1 is complete
+          WB_ACC(0, mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1)));   // our own dc store of frame t+1 is complete
           mbar_arrive(&dep_free[d]);
           const int b3 = (int)(it % 3);
           const uint32_t par3 = (uint32_t)((it / 3) & 1);
-          mbar_wait(&stg_free[b3], par3 ^ 1);                        // the stores of tile it-3 have left the buffer
-          if (it >= 2) mbar_wait(&stg_full[(it - 2) % 3], (uint32_t)(((it - 2) / 3) & 1));   // c buffer: math of it-2 done
+          WB_ACC(1, mbar_wait(&stg_free[b3], par3 ^ 1));             // the stores of tile it-3 have left the buffer
+          if (it >= 2) WB_ACC(2, mbar_wait(&stg_full[(it - 2) % 3], (uint32_t)(((it - 2) / 3) & 1)));   // c buffer: math of it-2 done
           uint8_t* sb = stg + b3 * kWbIoBytes;
-          uint8_t* cb = cst + buf * kWbCBytes;
-          mbar_expect_tx(&in_full[b3], kWbIoBytes + kWbCBytes);
+          uint8_t* cb = cst + buf * kWbCpBytes;
+          if (WB_ABL(32)) { mbar_arrive(&in_full[b3]); continue; }
+          mbar_expect_tx(&in_full[b3], kWbIoBytes + kWbCpBytes);
           tma_load_3d(sb + kWbOffG, &ly.t_dg, &in_full[b3], ns * 128, j * kWbTile, t);
           tma_load_3d(sb + kWbOffG + 8192, &ly.t_dg, &in_full[b3], ns * 128 + 64, j * kWbTile, t);
-          tma_load_3d(cb + kWbOffCt, &ly.t_c, &in_full[b3], ns * 32, j * kWbTile, t + 1);
-          tma_load_3d(cb + kWbOffCp, &ly.t_c, &in_full[b3], ns * 32, j * kWbTile, t);
+          tma_load_3d(cb, &ly.t_c, &in_full[b3], ns * 32, j * kWbTile, t);
           tma_load_3d(sb + kWbOffDc, &ly.t_dc, &in_full[b3], ns * 32, j * kWbTile, 0);
         }
       }
+      WB_ACC_OUT(2, 3);
     }
   } else if (warp == kWbWarpTma) {
     // ------------------------------------------------------------------ TMA producer (B operand = dG rows)
@@ -262,20 +314,21 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int d = (int)(it % kWbDeps);
-          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));
+          WB_ACC(0, mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1)));
           mbar_arrive(&dep_free[d]);
           const int slab = is_R ? t + 1 : t;
           for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], kWbStageBytes);
+            WB_ACC(1, mbar_wait(&empty[stage], phase ^ 1));
+            if (WB_ABL(4)) mbar_arrive(&full[stage]); else mbar_expect_tx(&full[stage], kWbStageBytes);
 #pragma unroll
             for (int k = 0; k < kWbKbPerStage; ++k)
-              tma_load_3d(ring + stage * kWbStageBytes + k * (kWbTile * 128), &ly.t_dg, &full[stage],
+              if (!WB_ABL(4)) tma_load_3d(ring + stage * kWbStageBytes + k * (kWbTile * 128), &ly.t_dg, &full[stage],
                           s * (kWbKb * 64) + (gi * kWbKbPerStage + k) * 64, j * kWbTile, slab);
             if (++stage == kWbStages) { stage = 0; phase ^= 1; }
           }
         }
       }
+      WB_ACC_OUT(5, 2);
     }
   } else if (warp == kWbWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (A = W^T slice in TMEM, bf16)
@@ -293,245 +346,241 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;
       WL_STAMP(0);
-      mbar_wait(&acc_empty[buf], upar ^ 1);
+      WB_ACC(0, mbar_wait(&acc_empty[buf], upar ^ 1));
       tc_fence_after();
-      WL_STAMP(1);
       for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
-        mbar_wait(&full[stage], phase);
+        WB_ACC(1, mbar_wait(&full[stage], phase));
         tc_fence_after();
-        if (gi == 0) WL_STAMP(2);
         if (gi == kWbKb / kWbKbPerStage - 1) WL_STAMP(3);
         const uint32_t lo = desc_lo0 + stage * (kWbStageBytes >> 4);
         const uint32_t a0 = tmem + gi * kWbKbPerStage * 32;
         const uint32_t dacc = tmem + kWbAccCol + buf * kWbTile;
 #pragma unroll
         for (int q = 0; q < 4 * kWbKbPerStage; ++q)
-          umma_f16_ts_lohi(dacc, a0 + q * 8, lo + (q >> 2) * ((kWbTile * 128) >> 4) + (q & 3) * 2, desc_hi, idesc,
+          if (!WB_ABL(1)) umma_f16_ts_lohi(dacc, a0 + q * 8, lo + (q >> 2) * ((kWbTile * 128) >> 4) + (q & 3) * 2, desc_hi, idesc,
                            q == 0 ? (gi != 0 ? 1u : 0u) : 1u);
         umma_commit(&empty[stage]);
         if (gi == kWbKb / kWbKbPerStage - 1) umma_commit(&acc_full[buf]);
         if (++stage == kWbStages) { stage = 0; phase ^= 1; }
       }
+#ifdef SVB_WB_ACCOUNT
+      if (it == total - 1) WB_ACC_OUT(7, 2);
+#endif
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ exchange warps: TMEM -> split-K reduction
-    // Two warps per TMEM lane quarter (= unit quarter of the tile), 32 rows each in two passes of 16.  The DSMEM
-    // exchange (24 KB out + 24 KB in per tile at ~17 B/clk) is the longest stage of the tile; it runs here,
-    // decoupled from the gate backward of the previous tile (math warps) and from the MMAs of the next.
+  } else if (warp >= kWbWarpXch && warp < kWbWarpXch + 4) {
+    // ------------------------------------------------------------------ exchange warps: TMEM -> staged quarters
+    // One warp per TMEM lane quarter (= unit quarter of the tile), 64 rows in two halves.  The quarter this CTA owns
+    // (q == s) is staged as fp32 for the math warps; the other three are staged as fp16 and pushed to their owner by
+    // lane 0 of the staging warp itself, half by half (2 KB bulk copies: the first half travels while the second is
+    // staged; no push thread, nobody waits for the slowest warp).
     const int q = warp & 3;
-    const int half = warp >> 2;                // rows [32 half, 32 half + 32)
     const bool owner = q == s;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const uint32_t recv_a = smem_u32(recv), dh_a = smem_u32(dhb);
-    const bool use_x = owner && has_x;
-    long long it = 0;
-    for (int t = T - 1; t >= 0; --t) {
-      for (int j = 0; j < nt; ++j, ++it) {
+    const uint32_t dslot = (uint32_t)((q - s - 1) & 3);          // index of the quarter in my send buffer
+    const uint32_t src0 = owner ? smem_u32(own) : smem_u32(send) + dslot * kWbQuarterBytes;
+    // receiver q keeps my quarter in slot (s - q - 1) mod 4 of its receive buffer
+    const uint32_t rdst0 = map_to_cta(smem_u32(recv) + (uint32_t)((s - q - 1) & 3) * kWbQuarterBytes, (uint32_t)q);
+    const uint32_t rbar0 = map_to_cta(smem_u32(recv_full), (uint32_t)q);
+    for (long long it = 0; it < total; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t upar = (uint32_t)((it >> 1) & 1);
+      // (debug stamps: the owner warp and the sender warp of the next quarter)
+      long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2 && lane == 0 && (q == s || q == ((s + 1) & 3))) ? trace_cta + (it % nt) * 16 : nullptr;
+      if (owner) WL_STAMP(4);
+      if (owner) WB_ACC(0, mbar_wait_warp(&consumed[buf], upar ^ 1));            // the math warps have read own[buf] of use k-1
+      else WB_ACC(0, mbar_wait_cluster_warp(&peer_free[buf], upar ^ 1));         // send[buf] has left, the receiver is free and armed
+      if (owner) WL_STAMP(5); else WL_STAMP(1);
+      WB_ACC(1, mbar_wait_warp(&acc_full[buf], upar));
+      tc_fence_after();
+      if (owner) WL_STAMP(6);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + kWbAccCol + buf * kWbTile + half * 32, v);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (WB_ABL(16)) {
+        } else if (owner) {
+          const uint32_t d = src0 + buf * kWbOwnBytes + half * 32 * 128 + lane * 4;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sts_f32(d + i * 128, v[i]);
+        } else {
+          const uint32_t d = src0 + buf * kWbSendBytes + half * 32 * 64 + lane * 2;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t pk = pack_f16x2(v[i], v[i + 1]);
+            sts_u16(d + i * 64, (uint16_t)(pk & 0xffffu));
+            sts_u16(d + (i + 1) * 64, (uint16_t)(pk >> 16));
+          }
+        }
+        if (!owner) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !WB_ABL(64))
+            dsmem_bulk_push(rdst0 + buf * kWbRecvBytes + half * (kWbQuarterBytes / 2),
+                            src0 + buf * kWbSendBytes + half * (kWbQuarterBytes / 2), kWbQuarterBytes / 2, rbar0 + buf * 8);
+        }
+      }
+      if (owner) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&send_ready[buf]);
+      }
+      if (owner) WL_STAMP(7); else WL_STAMP(2);
+    }
+    // quarter 0 and quarter 1 warps: one of them is the owner (consumed wait), the other a sender (peer_free wait)
+    if (lane == 0 && q == 0) WB_ACC_OUT(9, 2);
+    if (lane == 0 && q == 1) WB_ACC_OUT(12, 2);
+  } else if (warp < kWbMathWarps) {
+    // ------------------------------------------------------------------ math warps: split-K reduction (own fp32 quarter
+    // + three received fp16 quarters + dX of the layer above), then X: dX tile out; R: gate backward, in place.
+    // 16 warps, thread = (row, 4 units): with 8 warps of (row, 8 units) the two warps per scheduler could not hide their
+    // own latencies (3100 busy cycles per tile for ~420 instructions per thread).
+    const uint32_t stg_a = smem_u32(stg), own_a = smem_u32(own), recv_a = smem_u32(recv);
+    const int mt = threadIdx.x;                // 0..511
+    const int row = mt >> 3, ug = mt & 7;      // units 4 ug .. 4 ug + 3 of the CTA's 32
+    float bsum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    // Software pipeline (R, nt >= 2): step k reduces tile k (waits for the exchange of tile k, sends the credits)
+    // and THEN runs the gate backward of tile k - 1, so that the exchange loop (stage -> push -> reduce -> credit ->
+    // stage of the tile after next) does not contain the gate math.  With one tile per frame tile k's operands are the
+    // dG of tile k - 1: no look-ahead (lag 0).
+    const int lag = (is_R && nt >= 2) ? 1 : 0;
+    float dh[4] = {0.f, 0.f, 0.f, 0.f};          // reduced dL/dh of the tile whose gate backward is next
+    int t = T - 1, j = 0;                        // tile being reduced
+    int tg = T - 1, jg = 0;                      // tile whose gates are processed (lag tiles behind)
+    for (long long it = 0; it < total + lag; ++it) {
+      float dn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (it < total) {
         const int buf = (int)(it & 1);
         const uint32_t upar = (uint32_t)((it >> 1) & 1);
-        const int d = (int)(it % kWbDeps);
-        long long* tr = (trace_cta && t == T / 2 && lane == 0 && warp < 2) ? trace_cta + j * 16 : nullptr;
-        if (warp == 0) WL_STAMP(4);
-        const float4* xf = nullptr;
-        float4 xv[4];
-        if (owner && is_R) {
-          mbar_wait(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1));
-          if (use_x) {
-            // dX tile of the layer above, in flight while the partial sums arrive
-            xf = reinterpret_cast<const float4*>(p.layer[l + 1].xring) + ((size_t)((t % kWbXRing) * nt + j) * NS + ns) * 512 +
-                 (half * 8) * 32 + lane;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xv[k] = __ldcg(xf + k * 32);
-          }
+        long long* tr = (trace_cta && t == T / 2 && threadIdx.x == 0) ? trace_cta + j * 16 : nullptr;
+        WL_STAMP(8);
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* xrow = nullptr;
+        if (has_x) {
+          // dX tile of the layer above (L2-resident ring), in flight while the partial sums arrive
+          const int d = (int)(it % kWbDeps);
+          WB_ACC(0, mbar_wait_warp(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1)));
+          xrow = p.layer[l + 1].xring + (((size_t)((t % kWbXRing) * nt + j) * NS + ns) * kWbTile + row) * 32;
+          x0 = __ldcg(reinterpret_cast<const float4*>(xrow) + ug);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dep_free[d]);
+        } else if (is_R && t == T - 1 && j * kWbTile + row < p.B) {       // top layer, last frame: + dL/dh_last
+          x0 = __ldg(reinterpret_cast<const float4*>(p.dh_last + (size_t)(j * kWbTile + row) * H + ns * 32) + ug);
         }
-        if (warp == 0) WL_STAMP(5);
-        mbar_wait(&acc_full[buf], upar);
-        tc_fence_after();
-        if (warp == 0) WL_STAMP(6);
+        WB_ACC(1, mbar_wait_warp(&send_ready[buf], upar));
+        const float4 o0 = lds_f4(own_a + buf * kWbOwnBytes + row * 128 + ug * 16);
+        WL_STAMP(9);
+        if (!WB_ABL(64)) WB_ACC(2, mbar_wait_warp(&recv_full[buf], upar));
+        dn[0] = o0.x; dn[1] = o0.y; dn[2] = o0.z; dn[3] = o0.w;
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          const int rg0 = half * 8 + ps * 4;   // first 4-row group of this pass
-          float v[16];
-          tmem_ld16(tmem + lane_base + kWbAccCol + buf * kWbTile + rg0 * 4, v);
-          tmem_ld_wait();
-          if (ps == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        for (int sl = 0; sl < 3; ++sl) {
+          const uint2 r = lds_u2(recv_a + buf * kWbRecvBytes + sl * kWbQuarterBytes + row * 64 + ug * 8);
+          const float2 a0 = half2_to_float2(r.x), a1 = half2_to_float2(r.y);
+          dn[0] += a0.x; dn[1] += a0.y; dn[2] += a1.x; dn[3] += a1.y;
+        }
+        dn[0] += x0.x; dn[1] += x0.y; dn[2] += x0.z; dn[3] += x0.w;
+        // every math thread has its part of recv[buf] / own[buf] in registers: re-arm the receive barrier for the use
+        // after next, hand own[buf] back to the exchange warps, tell the three senders
+        WB_ACC(3, math_warps_sync());
+        if (warp == 0) {
+          if (lane == 0) {
+            if (it + 2 < total && !WB_ABL(64)) mbar_expect_tx(&recv_full[buf], kWbRecvBytes);
+            mbar_arrive(&consumed[buf]);
           }
-          if (!owner) {
-            // push this quarter of the partial sum to its owner (CTA q): slot (s - q - 1) mod 4 of its receive buffer
-            if (ps == 0) {
-              if (warp == 1) WL_STAMP(12);
-              mbar_wait_cluster(&peer_free[buf], upar ^ 1);
-              if (warp == 1) WL_STAMP(13);
-            }
-            const uint32_t dst = map_to_cta(recv_a + buf * kWbRecvBytes + ((s - q - 1) & 3) * 4096 + (rg0 >> 1) * 512 + lane * 16,
-                                            (uint32_t)q);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              st_cluster_u4(dst + k * 512, make_uint4(pack_f16x2(v[8 * k], v[8 * k + 1]), pack_f16x2(v[8 * k + 2], v[8 * k + 3]),
-                                                      pack_f16x2(v[8 * k + 4], v[8 * k + 5]), pack_f16x2(v[8 * k + 6], v[8 * k + 7])));
-            if (ps == 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive_remote(&recv_full[buf], (uint32_t)q);
-              if (warp == 1) WL_STAMP(14);
-            }
-            continue;
-          }
-          if (ps == 0) {
-            mbar_wait_cluster(&recv_full[buf], upar);
-            if (warp == 0) WL_STAMP(7);
-          }
-#pragma unroll
-          for (int sl = 0; sl < 3; ++sl)
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint4 r = lds_u4(recv_a + buf * kWbRecvBytes + sl * 4096 + ((rg0 >> 1) + k) * 512 + lane * 16);
-              const float2 a0 = half2_to_float2(r.x), a1 = half2_to_float2(r.y), a2 = half2_to_float2(r.z), a3 = half2_to_float2(r.w);
-              v[8 * k] += a0.x; v[8 * k + 1] += a0.y; v[8 * k + 2] += a1.x; v[8 * k + 3] += a1.y;
-              v[8 * k + 4] += a2.x; v[8 * k + 5] += a2.y; v[8 * k + 6] += a3.x; v[8 * k + 7] += a3.y;
-            }
-          if (ps == 1) {
-            __syncwarp();
-            // three lanes signal the three senders in parallel (a remote arrive is a ~1000-cycle round trip)
-            if (lane < 3) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
-          }
-          if (!is_R) {
-            // dX tile, fragment order [row group][lane] float4 = rows 4 rg .. 4 rg + 3 of unit `lane`: staged in shared
-            // memory (the epilogue staging area is unused in X) and bulk-copied to the ring by the signal thread -- a
-            // gpu-scope fence in these two warps after direct global stores cost ~2000 cycles of the tile's chain
-            if (ps == 0) mbar_wait(&x_taken[buf], upar ^ 1);       // the copy of tile it-2 has left the buffer
-            const uint32_t xo = smem_u32(stg) + buf * 8192 + (rg0 * 32 + lane) * 16;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sts_f4(xo + k * 512, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-            if (ps == 1) {
-              fence_proxy_async_smem();
-              mbar_arrive(&x_done[buf]);
-            }
-            continue;
-          }
-          if (use_x) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { v[4 * k] += xv[k].x; v[4 * k + 1] += xv[k].y; v[4 * k + 2] += xv[k].z; v[4 * k + 3] += xv[k].w; }
-            if (ps == 0) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) xv[k] = __ldcg(xf + (4 + k) * 32);
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&dep_free[d]);
-            }
+          __syncwarp();
+          if (lane < 3 && it + 2 < total) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
+        }
+        WL_STAMP(10);
 #ifndef SVB_NO_RING_DISCARD
-            else {
-              // the warp's 4 KB of the dX tile have been consumed: drop the lines from L2 without write-back (the ring
-              // is read exactly once, from L2; see the gin ring of wlstm.cuh).  Lane -> (row of 512 bytes, 128-byte line)
-              asm volatile("discard.global.L2 [%0], 128;" ::"l"(xf - lane + (lane >> 2) * 32 + (lane & 3) * 8) : "memory");
-            }
+        // the dX row has been consumed: drop its line from L2 without write-back (the ring is read exactly once, from L2)
+        if (has_x && ug == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(xrow) : "memory");
 #endif
-          } else {
-            if (ps == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&dep_free[d]); }
-            if (l == p.L - 1 && t == T - 1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int m = j * kWbTile + rg0 * 4 + i;
-                if (m < p.B) v[i] += __ldg(p.dh_last + (size_t)m * H + ns * 32 + lane);
-              }
-            }
-          }
-          // reduced dh tile [row][unit] fp32 for the gate backward (math warps)
-          if (ps == 0) mbar_wait(&dh_free[buf], upar ^ 1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) sts_f32(dh_a + buf * kWbDhBytes + (rg0 * 4 + i) * 128 + lane * 4, v[i]);
-          if (ps == 1) mbar_arrive(&dh_full[buf]);
-        }
-        if (warp == 0) WL_STAMP(8);
-      }
-    }
-  } else if (warp < kWbEpiWarps) {
-    // ------------------------------------------------------------------ math warps (R): gate backward, in place
-    if (is_R) {
-      const uint32_t dh_a = smem_u32(dhb), stg_a = smem_u32(stg);
-      const int mt = threadIdx.x - 256;          // 0..255 -> (row, 8 consecutive units as two groups of 4)
-      const int row = mt >> 2;
-      float bsum[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) bsum[i] = 0.f;
-      long long it = 0;
-      for (int t = T - 1; t >= 0; --t) {
-        for (int j = 0; j < nt; ++j, ++it) {
-          const int buf = (int)(it & 1);
-          const uint32_t upar = (uint32_t)((it >> 1) & 1);
-          long long* tr = (trace_cta && t == T / 2 && threadIdx.x == 256) ? trace_cta + j * 16 : nullptr;
-          WL_STAMP(9);
-          mbar_wait(&dh_full[buf], upar);
-          const int b3 = (int)(it % 3);
-          const uint32_t par3 = (uint32_t)((it / 3) & 1);
-          mbar_wait(&in_full[b3], par3);
-          WL_STAMP(10);
-          const uint32_t sb = stg_a + b3 * kWbIoBytes;
-          const uint32_t cb = stg_a + 3 * kWbIoBytes + buf * kWbCBytes;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int ug = (mt & 3) * 2 + hh;      // units 4 ug .. 4 ug + 3 of the CTA's 32
-            const int G = ug >> 1;                 // group of 8 units
-            const uint32_t g_off = (G >> 1) * 8192 + row * 128 + 8 * (ug & 1);
-            const uint32_t u_off = row * 128 + ((ug ^ (row & 7)) << 4);
-            const float4 dh4 = lds_f4(dh_a + buf * kWbDhBytes + row * 128 + ug * 16);
-            const float4 ct4 = lds_f4(cb + kWbOffCt + u_off), cp4 = lds_f4(cb + kWbOffCp + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
-            uint32_t gaddr[4];
-            uint2 gq[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              gaddr[g] = sb + kWbOffG + g_off + (((4 * (G & 1) + g) ^ (row & 7)) << 4);
-              gq[g] = lds_u2(gaddr[g]);
-            }
-            const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, ct[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
-            const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcs[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
-            float gi[4], gf[4], gg[4], go[4], di[4], df[4], dg[4], dO[4], dcn[4];
-            // the stash holds the activations as fp16 (pack8_stash); dG goes back in place as bf16
-            { const float2 a = half2_to_float2(gq[0].x), b = half2_to_float2(gq[0].y); gi[0] = a.x; gi[1] = a.y; gi[2] = b.x; gi[3] = b.y; }
-            { const float2 a = half2_to_float2(gq[1].x), b = half2_to_float2(gq[1].y); gf[0] = a.x; gf[1] = a.y; gf[2] = b.x; gf[3] = b.y; }
-            { const float2 a = half2_to_float2(gq[2].x), b = half2_to_float2(gq[2].y); gg[0] = a.x; gg[1] = a.y; gg[2] = b.x; gg[3] = b.y; }
-            { const float2 a = half2_to_float2(gq[3].x), b = half2_to_float2(gq[3].y); go[0] = a.x; go[1] = a.y; go[2] = b.x; go[3] = b.y; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float tc = tanh_approx(ct[i]);
-              const float dc = dh[i] * go[i] * (1.f - tc * tc) + dcs[i];
-              dO[i] = dh[i] * tc * go[i] * (1.f - go[i]);
-              di[i] = dc * gg[i] * gi[i] * (1.f - gi[i]);
-              df[i] = dc * cp[i] * gf[i] * (1.f - gf[i]);
-              dg[i] = dc * gi[i] * (1.f - gg[i] * gg[i]);
-              dcn[i] = dc * gf[i];
-            }
-            // bias gradients: per-thread partial column sums of dG over all tiles and frames (reduced over the 64 rows
-            // once, at the end of the kernel)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              bsum[hh * 16 + i] += di[i]; bsum[hh * 16 + 4 + i] += df[i];
-              bsum[hh * 16 + 8 + i] += dg[i]; bsum[hh * 16 + 12 + i] += dO[i];
-            }
-            sts_u2(gaddr[0], make_uint2(pack_bf16x2(di[0], di[1]), pack_bf16x2(di[2], di[3])));
-            sts_u2(gaddr[1], make_uint2(pack_bf16x2(df[0], df[1]), pack_bf16x2(df[2], df[3])));
-            sts_u2(gaddr[2], make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3])));
-            sts_u2(gaddr[3], make_uint2(pack_bf16x2(dO[0], dO[1]), pack_bf16x2(dO[2], dO[3])));
-            sts_f4(sb + kWbOffDc + u_off, make_float4(dcn[0], dcn[1], dcn[2], dcn[3]));
-          }
-          mbar_arrive(&dh_free[buf]);
+        if (!is_R) {
+          // dX tile [row][32 units] fp32: staged in shared memory (the epilogue staging area is unused in X) and
+          // bulk-copied to the ring by the signal thread
+          WB_ACC(4, mbar_wait_warp(&x_taken[buf], upar ^ 1));    // the copy of tile it-2 has left the buffer
+          sts_f4(stg_a + buf * 8192 + row * 128 + ug * 16, make_float4(dn[0], dn[1], dn[2], dn[3]));
           fence_proxy_async_smem();
-          mbar_arrive(&stg_full[b3]);
-          WL_STAMP(11);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&x_done[buf]);
         }
+        if (++j == nt) { j = 0; --t; }
       }
+      if (lag == 0) { dh[0] = dn[0]; dh[1] = dn[1]; dh[2] = dn[2]; dh[3] = dn[3]; }
+      if (is_R && it >= lag) {
+        const long long ig = it - lag;             // tile (tg, jg)
+        const int bufg = (int)(ig & 1);
+        long long* tr = (trace_cta && tg == T / 2 && threadIdx.x == 0) ? trace_cta + jg * 16 : nullptr;
+        const int b3 = (int)(ig % 3);
+        const uint32_t par3 = (uint32_t)((ig / 3) & 1);
+        WB_ACC(4, mbar_wait_warp(&in_full[b3], par3));
+        WL_STAMP(11);
+        const uint32_t sb = stg_a + b3 * kWbIoBytes;
+        const uint32_t cb = stg_a + kWbIo * kWbIoBytes + bufg * kWbCpBytes;
+        if (!WB_ABL(2)) {
+          const int G = ug >> 1;                 // group of 8 units
+          const uint32_t g_off = (G >> 1) * 8192 + row * 128 + 8 * (ug & 1);
+          const uint32_t u_off = row * 128 + ((ug ^ (row & 7)) << 4);
+          const float4 cp4 = lds_f4(cb + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
+          uint32_t gaddr[4];
+          uint2 gq[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            gaddr[g] = sb + kWbOffG + g_off + (((4 * (G & 1) + g) ^ (row & 7)) << 4);
+            gq[g] = lds_u2(gaddr[g]);
+          }
+          const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcs[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+          float gi[4], gf[4], gg[4], go[4], di[4], df[4], dg[4], dO[4], dcn[4];
+          // the stash holds the activations as fp16 (pack8_stash); dG goes back in place as bf16
+          { const float2 a = half2_to_float2(gq[0].x), b = half2_to_float2(gq[0].y); gi[0] = a.x; gi[1] = a.y; gi[2] = b.x; gi[3] = b.y; }
+          { const float2 a = half2_to_float2(gq[1].x), b = half2_to_float2(gq[1].y); gf[0] = a.x; gf[1] = a.y; gf[2] = b.x; gf[3] = b.y; }
+          { const float2 a = half2_to_float2(gq[2].x), b = half2_to_float2(gq[2].y); gg[0] = a.x; gg[1] = a.y; gg[2] = b.x; gg[3] = b.y; }
+          { const float2 a = half2_to_float2(gq[3].x), b = half2_to_float2(gq[3].y); go[0] = a.x; go[1] = a.y; go[2] = b.x; go[3] = b.y; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float tc = tanh_approx(fmaf(gf[i], cp[i], gi[i] * gg[i]));     // tanh(c_t), c_t = f c_{t-1} + i g
+            const float dc = dh[i] * go[i] * (1.f - tc * tc) + dcs[i];
+            dO[i] = dh[i] * tc * go[i] * (1.f - go[i]);
+            di[i] = dc * gg[i] * gi[i] * (1.f - gi[i]);
+            df[i] = dc * cp[i] * gf[i] * (1.f - gf[i]);
+            dg[i] = dc * gi[i] * (1.f - gg[i] * gg[i]);
+            dcn[i] = dc * gf[i];
+          }
+          // bias gradients: per-thread partial column sums of dG over all tiles and frames (reduced over the 64 rows
+          // once, at the end of the kernel)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            bsum[i] += di[i]; bsum[4 + i] += df[i]; bsum[8 + i] += dg[i]; bsum[12 + i] += dO[i];
+          }
+          sts_u2(gaddr[0], make_uint2(pack_bf16x2(di[0], di[1]), pack_bf16x2(di[2], di[3])));
+          sts_u2(gaddr[1], make_uint2(pack_bf16x2(df[0], df[1]), pack_bf16x2(df[2], df[3])));
+          sts_u2(gaddr[2], make_uint2(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3])));
+          sts_u2(gaddr[3], make_uint2(pack_bf16x2(dO[0], dO[1]), pack_bf16x2(dO[2], dO[3])));
+          sts_f4(sb + kWbOffDc + u_off, make_float4(dcn[0], dcn[1], dcn[2], dcn[3]));
+        }
+        if (!WB_ABL(256)) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_full[b3]);
+        WL_STAMP(14);
+        if (++jg == nt) { jg = 0; --tg; }
+      }
+      dh[0] = dn[0]; dh[1] = dn[1]; dh[2] = dn[2]; dh[3] = dn[3];
+    }
+    if (threadIdx.x == 0) WB_ACC_OUT(14, 5);
+    if (is_R) {
       // partial sums -> shared memory [row][packed column] (the operand ring is idle by now: the last MMA of this CTA
       // completed before the last accumulator was handed to the exchange warps)
       float* bsc = reinterpret_cast<float*>(ring);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int ug = (mt & 3) * 2 + hh;
+      for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) bsc[row * 128 + 32 * (ug >> 1) + 8 * g + 4 * (ug & 1) + i] = bsum[hh * 16 + g * 4 + i];
-      }
+        for (int i = 0; i < 4; ++i) bsc[row * 128 + 32 * (ug >> 1) + 8 * g + 4 * (ug & 1) + i] = bsum[g * 4 + i];
     }
   } else if (warp == kWbWarpStore && !is_R) {
     // ------------------------------------------------------------------ signal thread (X): publish dX tiles (lazily,
@@ -592,16 +641,18 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
             if (ptr_tr) *ptr_tr = clock64();
             pend = false;
           }
-          mbar_wait(&stg_full[b3], par3);
+          WB_ACC(0, mbar_wait(&stg_full[b3], par3));
           const uint8_t* sb = stg + b3 * kWbIoBytes;
-          tma_store_3d(&ly.t_dg, sb + kWbOffG, ns * 128, j * kWbTile, t);
-          tma_store_3d(&ly.t_dg, sb + kWbOffG + 8192, ns * 128 + 64, j * kWbTile, t);
-          tma_store_3d(&ly.t_dc, sb + kWbOffDc, ns * 32, j * kWbTile, 0);
+          if (!WB_ABL(128)) {
+            tma_store_3d(&ly.t_dg, sb + kWbOffG, ns * 128, j * kWbTile, t);
+            tma_store_3d(&ly.t_dg, sb + kWbOffG + 8192, ns * 128 + 64, j * kWbTile, t);
+            tma_store_3d(&ly.t_dc, sb + kWbOffDc, ns * 32, j * kWbTile, 0);
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          WB_ACC(1, asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"));
           mbar_arrive(&stg_free[b3]);
           if (pend) {
-            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            WB_ACC(2, asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"));
             red_release_add(pflag, 1u);
             if (ptr_tr) *ptr_tr = clock64();
           }
@@ -615,6 +666,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         red_release_add(pflag, 1u);
         if (ptr_tr) *ptr_tr = clock64();
       }
+      WB_ACC_OUT(19, 3);
     }
   }
   tc_fence_before();
@@ -632,7 +684,14 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   }
   cluster_sync_all();                          // no CTA leaves while a peer may still push into or signal it
   if (warp == kWbWarpMma) tmem_dealloc<512>(tmem);
-  if (p.trace && threadIdx.x == 0) p.trace[2 * nt * 16 + blockIdx.x] = clock64() - t_cta0;
+  if (p.trace && threadIdx.x == 0) {
+    p.trace[2 * nt * 16 + blockIdx.x] = clock64() - t_cta0;
+#ifdef SVB_WB_ACCOUNT
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[2 * nt * 16 + 256 + 32 * blockIdx.x + 31] = smid;
+#endif
+  }
 }
 
 // Largest number of 4-CTA clusters of the kernel that can be co-resident on the current device (0 on error).

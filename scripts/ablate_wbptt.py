@@ -1,4 +1,5 @@
-"""Dev: time the persistent BPTT kernel with parts switched off (results are garbage in those runs)."""
+"""Dev: time the persistent BPTT kernel with parts switched off (results are garbage in those runs).  Needs the
+accounting build: make -C pytorch_speaker_verification_b200/csrc ALT=1 ALTFLAGS=-DSVB_WB_ACCOUNT, SVB_LIB_PATH=.../libsvb200_alt.so."""
 import sys
 import torch
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
@@ -11,7 +12,7 @@ net = svb.SpeechEmbedder().cuda()
 x = torch.tensor(I.logmel(640, 160, seed=1234)).cuda()
 import ctypes
 buf = (ctypes.c_float * 16)()
-for mask in (0, 1, 2, 4, 16, 32, 8, 63, 55, 47):
+for mask in (0, 1, 2, 4, 8, 16, 32, 128, 256, 2 + 256, 1 + 4, 2 + 32 + 128 + 256, 1 + 4 + 16, 511 - 64 - 8, 511 - 64):
     res = []
     for rep in range(3):
         net.zero_grad()
@@ -23,5 +24,5 @@ for mask in (0, 1, 2, 4, 16, 32, 8, 63, 55, 47):
         torch.cuda.synchronize()
         L.svb_profile_read(buf, 16)
         res.append(buf[5])
-    print(f"ablate={mask:3d} (1 MMA, 2 math, 4 operand loads, 16 DSMEM payload, 32 input loads, 8 deps): BPTT kernel {min(res):.3f} ms", flush=True)
+    print(f"ablate={mask:3d} (1 MMA, 2 math, 4 operand loads, 8 deps, 16 staging stores, 32 input loads, 64 push, 128 stores, 256 math fence): BPTT kernel {min(res):.3f} ms", flush=True)
 L.svb_set_ablate(0); L.svb_profile_enable(0)

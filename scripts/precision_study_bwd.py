@@ -50,7 +50,7 @@ def forward(x, sd, L=3):
     return y, st
 
 
-def backward(dh_last, st, sd, stash="bf16", dgm="bf16", wm="bf16", part="fp16", hm="bf16", L=3):
+def backward(dh_last, st, sd, stash="bf16", dgm="bf16", wm="bf16", part="fp16", hm="bf16", L=3, recompute_c=False):
     grads = {}
     B, T = st[0][0].shape[:2]
     dx_above = None
@@ -73,7 +73,8 @@ def backward(dh_last, st, sd, stash="bf16", dgm="bf16", wm="bf16", part="fp16", 
             elif t == T - 1:
                 dh = dh + dh_last
             i, f, gg, o = (rnd(v, stash) for v in gs[t])
-            tc = torch.tanh(cs[t + 1])
+            # recompute_c: c_t = f c_{t-1} + i g from the ROUNDED stash instead of reading the stored fp32 c_t
+            tc = torch.tanh(f * cs[t] + i * gg if recompute_c else cs[t + 1])
             dc = dh * o * (1 - tc * tc) + dc_run
             dO = dh * tc * o * (1 - o)
             di = dc * gg * i * (1 - i)
@@ -121,6 +122,9 @@ def main():
         "stash fp16, W exact": ("fp16", "bf16", "exact", "fp16", "bf16"),
         "stash fp16, partials exact": ("fp16", "bf16", "bf16", "exact", "bf16"),
         "stash fp16, h exact": ("fp16", "bf16", "bf16", "fp16", "exact"),
+        "stash fp16, c_t recomputed from the stash": ("fp16", "bf16", "bf16", "fp16", "bf16", 3, True),
+        "only stash fp16 + c_t recomputed": ("fp16", "exact", "exact", "exact", "exact", 3, True),
+        "only stash fp16": ("fp16", "exact", "exact", "exact", "exact"),
         "only stash bf16": ("bf16", "exact", "exact", "exact", "exact"),
         "only dG bf16": ("exact", "bf16", "exact", "exact", "exact"),
         "only W bf16": ("exact", "exact", "bf16", "exact", "exact"),

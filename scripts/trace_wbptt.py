@@ -20,9 +20,11 @@ for i in range(3):
 L.svb_set_trace_bwd(None)
 dur = buf[2 * nt * 16:].cpu().numpy()
 t = buf[:2 * nt * 16].cpu().numpy().reshape(2, nt, 16).astype(np.float64)
-names = ["mma_start", "mma_accfree", "mma_full0", "mma_fullL", "epi_start", "epi_dep_ok", "epi_accfull", "own_recv_ok",
-         "own_reduced", "bar_done", "in_full_ok", "epi_done", "snd_start", "snd_peer_ok", "snd_sent", "store_done"]
-for r, tag in enumerate(("R(1,0,0)", "X(1,0,0)")):
+names = ["mma_start", "snd_bufs_ok", "snd_staged", "mma_fullL", "xch_start", "xch_bufs_ok", "xch_accfull", "xch_staged",
+         "math_start", "math_own_ok", "math_reduced", "math_in_full", "push_ready", "push_issued", "math_done", "store_done"]
+import os
+TL = os.environ.get("SVB_TRACE_LAYER", "1")
+for r, tag in enumerate((f"R({TL},0,0)", f"X({TL},0,0)")):
     t0 = t[r][t[r] > 0].min()
     print(tag)
     print("      " + " ".join(f"{n[:11]:>11s}" for n in names))
