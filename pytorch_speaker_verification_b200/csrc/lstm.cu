@@ -1005,7 +1005,8 @@ extern "C" int svb_embedder_backward(const float* demb, const void* packed, cons
     const int num_sms = device_sm_count();
     // all (2L - 1) * H/128 clusters of 4 must be co-resident: ask the occupancy calculator (clusters of 4 strand SMs
     // at GPC boundaries: 33 fit the 148 SMs of a B200), else the per-frame path below
-    use_wbptt = num_sms >= 4 * (2 * L - 1) * (H / 128) && wbptt_max_clusters<768>() >= (2 * L - 1) * (H / 128);
+    use_wbptt = num_sms >= 4 * (2 * L - 1) * (H / 128) && wbptt_max_clusters<768>() >= (2 * L - 1) * (H / 128) &&
+                (long long)T * ((B + kWbTile - 1) / kWbTile) < (1LL << 30);   // (32-bit tile counters in the kernel)
   }
   if (use_wbptt) {
     // ---- BPTT of the whole stack (recurrent products, dX products, gate backward) in one persistent kernel

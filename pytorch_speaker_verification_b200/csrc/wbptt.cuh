@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   const int ns = 4 * u + s;                    // 32-unit slice index within the layer
   const WbLayer& ly = p.layer[l];
   const int nt = p.nt, T = p.T;
-  const long long total = (long long)T * nt;
+  const int total = T * nt;                   // (< 2^31: checked by the launcher; 32-bit tile counters keep the per-tile bookkeeping short)
   const bool has_x = is_R && l + 1 < p.L;      // dX from the layer above arrives through its ring
   // debug trace: R(l, 0, 0) rows [0, nt), X(l, 0, 0) rows [nt, 2 nt): 16 clock64 stamps per tile of frame T/2
   long long* const trace_cta = (p.trace && l == p.trace_l && u == p.trace_u && s == p.trace_s) ? p.trace + (is_R ? 0 : (size_t)nt * 16) : nullptr;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
 
   if (warp == kWbWarpPoll && lane == 0) {
     // ------------------------------------------------------------------ dependency poller
-    long long it = 0;
+    int it = 0;
     for (int t = T - 1; t >= 0; --t) {
       for (int j = 0; j < nt; ++j, ++it) {
         const int d = (int)(it % kWbDeps);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   } else if (warp == kWbWarpLoad && lane == 0) {
     // ------------------------------------------------------------------ epilogue-input loader (R only)
     if (is_R) {
-      long long it = 0;
+      int it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int buf = (int)(it & 1);
@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           mbar_arrive(&dep_free[d]);
           const int b3 = (int)(it % 3);
           const uint32_t par3 = (uint32_t)((it / 3) & 1);
-          WB_ACC(1, mbar_wait(&stg_free[b3], par3 ^ 1));             // the stores of tile it-3 have left the buffer
-          if (it >= 2) WB_ACC(2, mbar_wait(&stg_full[(it - 2) % 3], (uint32_t)(((it - 2) / 3) & 1)));   // c buffer: math of it-2 done
+          if (!WB_ABL(2048)) WB_ACC(1, mbar_wait(&stg_free[b3], par3 ^ 1));             // the stores of tile it-3 have left the buffer
+          if (it >= 2 && !WB_ABL(2048)) WB_ACC(2, mbar_wait(&stg_full[(it - 2) % 3], (uint32_t)(((it - 2) / 3) & 1)));   // c buffer: math of it-2 done
           uint8_t* sb = stg + b3 * kWbIoBytes;
           uint8_t* cb = cst + buf * kWbCpBytes;
           if (WB_ABL(32)) { mbar_arrive(&in_full[b3]); continue; }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      long long it = 0;
+      int it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int d = (int)(it % kWbDeps);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           mbar_arrive(&dep_free[d]);
           const int slab = is_R ? t + 1 : t;
           for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
-            WB_ACC(1, mbar_wait(&empty[stage], phase ^ 1));
+            if (!WB_ABL(32768)) WB_ACC(1, mbar_wait(&empty[stage], phase ^ 1));
             if (WB_ABL(4)) mbar_arrive(&full[stage]); else mbar_expect_tx(&full[stage], kWbStageBytes);
 #pragma unroll
             for (int k = 0; k < kWbKbPerStage; ++k)
@@ -341,15 +341,15 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     // the compiler treats the body as divergent code and wraps EVERY tcgen05.mma in an elect / R2UR.BROADCAST /
     // BRA.U.ANY loop (~12 instructions, 60-70 cycles of issue per MMA instead of 32).
     if (elect_one())
-    for (long long it = 0; it < total; ++it) {
+    for (int it = 0; it < total; ++it) {
       const int buf = (int)(it & 1);
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2) ? trace_cta + (it % nt) * 16 : nullptr;
       WL_STAMP(0);
-      WB_ACC(0, mbar_wait(&acc_empty[buf], upar ^ 1));
+      if (!WB_ABL(16384)) WB_ACC(0, mbar_wait(&acc_empty[buf], upar ^ 1));
       tc_fence_after();
       for (int gi = 0; gi < kWbKb / kWbKbPerStage; ++gi) {
-        WB_ACC(1, mbar_wait(&full[stage], phase));
+        if (!WB_ABL(32768)) WB_ACC(1, mbar_wait(&full[stage], phase));
         tc_fence_after();
         if (gi == kWbKb / kWbKbPerStage - 1) WL_STAMP(3);
         const uint32_t lo = desc_lo0 + stage * (kWbStageBytes >> 4);
@@ -381,16 +381,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     // receiver q keeps my quarter in slot (s - q - 1) mod 4 of its receive buffer
     const uint32_t rdst0 = map_to_cta(smem_u32(recv) + (uint32_t)((s - q - 1) & 3) * kWbQuarterBytes, (uint32_t)q);
     const uint32_t rbar0 = map_to_cta(smem_u32(recv_full), (uint32_t)q);
-    for (long long it = 0; it < total; ++it) {
+    for (int it = 0; it < total; ++it) {
       const int buf = (int)(it & 1);
       const uint32_t upar = (uint32_t)((it >> 1) & 1);
       // (debug stamps: the owner warp and the sender warp of the next quarter)
       long long* tr = (trace_cta && (T - 1 - it / nt) == T / 2 && lane == 0 && (q == s || q == ((s + 1) & 3))) ? trace_cta + (it % nt) * 16 : nullptr;
       if (owner) WL_STAMP(4);
-      if (owner) WB_ACC(0, mbar_wait_warp(&consumed[buf], upar ^ 1));            // the math warps have read own[buf] of use k-1
-      else WB_ACC(0, mbar_wait_cluster_warp(&peer_free[buf], upar ^ 1));         // send[buf] has left, the receiver is free and armed
+      if (WB_ABL(512)) {
+      } else if (owner) WB_ACC(0, mbar_wait_warp(&consumed[buf], upar ^ 1));            // the math warps have read own[buf] of use k-1
+      else if (!WB_ABL(64)) WB_ACC(0, mbar_wait_cluster_warp(&peer_free[buf], upar ^ 1));         // send[buf] has left, the receiver is free and armed
       if (owner) WL_STAMP(5); else WL_STAMP(1);
-      WB_ACC(1, mbar_wait_warp(&acc_full[buf], upar));
+      if (!WB_ABL(65536)) WB_ACC(1, mbar_wait_warp(&acc_full[buf], upar));
       tc_fence_after();
       if (owner) WL_STAMP(6);
 #pragma unroll
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     float dh[4] = {0.f, 0.f, 0.f, 0.f};          // reduced dL/dh of the tile whose gate backward is next
     int t = T - 1, j = 0;                        // tile being reduced
     int tg = T - 1, jg = 0;                      // tile whose gates are processed (lag tiles behind)
-    for (long long it = 0; it < total + lag; ++it) {
+    for (int it = 0; it < total + lag; ++it) {
       float dn[4] = {0.f, 0.f, 0.f, 0.f};
       if (it < total) {
         const int buf = (int)(it & 1);
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         } else if (is_R && t == T - 1 && j * kWbTile + row < p.B) {       // top layer, last frame: + dL/dh_last
           x0 = __ldg(reinterpret_cast<const float4*>(p.dh_last + (size_t)(j * kWbTile + row) * H + ns * 32) + ug);
         }
-        WB_ACC(1, mbar_wait_warp(&send_ready[buf], upar));
+        if (!WB_ABL(8192)) WB_ACC(1, mbar_wait_warp(&send_ready[buf], upar));
         const float4 o0 = lds_f4(own_a + buf * kWbOwnBytes + row * 128 + ug * 16);
         WL_STAMP(9);
         if (!WB_ABL(64)) WB_ACC(2, mbar_wait_warp(&recv_full[buf], upar));
@@ -487,14 +488,14 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         dn[0] += x0.x; dn[1] += x0.y; dn[2] += x0.z; dn[3] += x0.w;
         // every math thread has its part of recv[buf] / own[buf] in registers: re-arm the receive barrier for the use
         // after next, hand own[buf] back to the exchange warps, tell the three senders
-        WB_ACC(3, math_warps_sync());
+        if (!WB_ABL(131072)) WB_ACC(3, math_warps_sync());
         if (warp == 0) {
           if (lane == 0) {
             if (it + 2 < total && !WB_ABL(64)) mbar_expect_tx(&recv_full[buf], kWbRecvBytes);
             mbar_arrive(&consumed[buf]);
           }
           __syncwarp();
-          if (lane < 3 && it + 2 < total) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
+          if (lane < 3 && it + 2 < total && !WB_ABL(64)) mbar_arrive_remote_relaxed(&peer_free[buf], (uint32_t)((s + 1 + lane) & 3));
         }
         WL_STAMP(10);
 #ifndef SVB_NO_RING_DISCARD
@@ -514,12 +515,12 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       }
       if (lag == 0) { dh[0] = dn[0]; dh[1] = dn[1]; dh[2] = dn[2]; dh[3] = dn[3]; }
       if (is_R && it >= lag) {
-        const long long ig = it - lag;             // tile (tg, jg)
+        const int ig = it - lag;                   // tile (tg, jg)
         const int bufg = (int)(ig & 1);
         long long* tr = (trace_cta && tg == T / 2 && threadIdx.x == 0) ? trace_cta + jg * 16 : nullptr;
         const int b3 = (int)(ig % 3);
         const uint32_t par3 = (uint32_t)((ig / 3) & 1);
-        WB_ACC(4, mbar_wait_warp(&in_full[b3], par3));
+        if (!WB_ABL(1024)) WB_ACC(4, mbar_wait_warp(&in_full[b3], par3));
         WL_STAMP(11);
         const uint32_t sb = stg_a + b3 * kWbIoBytes;
         const uint32_t cb = stg_a + kWbIo * kWbIoBytes + bufg * kWbCpBytes;
@@ -589,10 +590,10 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       bool pend = false;
       unsigned* pflag = nullptr;
       unsigned pval = 0;
-      for (long long it = 0; it < total; ++it) {
+      int t = T - 1, j = 0;
+      for (int it = 0; it < total; ++it) {
         const int buf = (int)(it & 1);
         const uint32_t upar = (uint32_t)((it >> 1) & 1);
-        const int t = T - 1 - (int)(it / nt), j = (int)(it % nt);
         if (pend && !mbar_test_wait(&x_done[buf], upar)) {
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(pflag), "r"(pval) : "memory");
@@ -611,7 +612,8 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         }
         pend = true;
         pflag = p.xcnt + ((size_t)l * NS + ns) * nt + j;
-        pval = (unsigned)(it / nt + 1);
+        pval = (unsigned)(T - t);
+        if (++j == nt) { j = 0; --t; }
       }
       if (pend) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -630,11 +632,12 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
       bool pend = false;
       unsigned* pflag = nullptr;
       long long* ptr_tr = nullptr;
-      long long it = 0;
+      int it = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int j = 0; j < nt; ++j, ++it) {
           const int b3 = (int)(it % kWbIo);
           const uint32_t par3 = (uint32_t)((it / kWbIo) & 1);
+          if (WB_ABL(4096)) pend = false;
           if (pend && !mbar_test_wait(&stg_full[b3], par3)) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             red_release_add(pflag, 1u);      // release: see wlstm.cuh
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           WB_ACC(1, asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"));
           mbar_arrive(&stg_free[b3]);
-          if (pend) {
+          if (pend && !WB_ABL(4096)) {
             WB_ACC(2, asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"));
             red_release_add(pflag, 1u);
             if (ptr_tr) *ptr_tr = clock64();

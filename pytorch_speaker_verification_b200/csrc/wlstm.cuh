@@ -240,9 +240,9 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], kWlEpiWarps / 2);        // one epilogue group (8 warps) per accumulator buffer
       mbar_init(&cin_full[b], 1);
-      mbar_init(&stg_full[b], 16 * kWlEpiWarps);
+      mbar_init(&stg_full[b], kWlEpiWarps / 2);         // one arrive per warp of the group (N arrivals on one mbarrier serialise)
       mbar_init(&stg_free[b], 1);
-      mbar_init(&gin_done[b], 16 * kWlEpiWarps);
+      mbar_init(&gin_done[b], kWlEpiWarps / 2);
       mbar_init(&gin_taken[b], 1);
     }
     for (int d = 0; d < kWlDeps; ++d) {
@@ -495,7 +495,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
           sts_f4(gs + 16384 + k * 2048, make_float4(a1[4 * k] + bias, a1[4 * k + 1] + bias, a1[4 * k + 2] + bias, a1[4 * k + 3] + bias));
         }
         fence_proxy_async_smem();
-        mbar_arrive(&gin_done[buf]);              // the signal warp copies and publishes the tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gin_done[buf]);   // the signal warp copies and publishes the tile
         WL_STAMP(13);
         continue;
       }
@@ -594,7 +595,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
       }
       if (p.ablate & 2) mbar_wait(&cin_full[buf], upar);
       fence_proxy_async_smem();
-      mbar_arrive(&stg_full[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stg_full[buf]);
       WL_STAMP(13);
     }
   } else if (warp == kWlWarpStore && !is_R) {

@@ -12,11 +12,17 @@ B, T = 640, 160
 x = torch.tensor(I.logmel(B, T, seed=1234)).cuda()
 nt = (B + 63) // 64
 buf = torch.zeros(2 * nt * 16 + 256, dtype=torch.int64, device="cuda")
+import os
+ABL = int(os.environ.get("SVB_ABLATE", "0"))     # (accounting build only: parts of the kernel switched off)
 for i in range(3):
     if i == 2: L.svb_set_trace_bwd(ctypes.c_void_p(buf.data_ptr()))
     net.zero_grad()
-    e = net(x); e.square().sum().backward()
+    L.svb_set_ablate(0)
+    e = net(x); loss = e.square().sum()
+    L.svb_set_ablate(ABL)
+    loss.backward()
     torch.cuda.synchronize()
+L.svb_set_ablate(0)
 L.svb_set_trace_bwd(None)
 dur = buf[2 * nt * 16:].cpu().numpy()
 t = buf[:2 * nt * 16].cpu().numpy().reshape(2, nt, 16).astype(np.float64)
