@@ -103,10 +103,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(SVB_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -142,6 +142,26 @@ __device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t p
   mbar_wait_cluster(bar, parity);
 #endif
 }
+// stores with the offset as an immediate (the staging loops are fully unrolled: one STS per element, no address adds)
+template <int kOff> __device__ __forceinline__ void sts_f32_imm(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(addr), "f"(v), "n"(kOff) : "memory");
+}
+template <int kOff> __device__ __forceinline__ void sts_u16_imm(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(addr), "h"(v), "n"(kOff) : "memory");
+}
+template <int I> struct WbStage {   // element I, I + 1 of a 32-row half: rows I and I + 1 of the lane's unit
+  static __device__ __forceinline__ void own(uint32_t d, const float (&v)[32]) {
+    sts_f32_imm<I * 128>(d, v[I]);
+    sts_f32_imm<(I + 1) * 128>(d, v[I + 1]);
+    if constexpr (I + 2 < 32) WbStage<I + 2>::own(d, v);
+  }
+  static __device__ __forceinline__ void send(uint32_t d, const float (&v)[32]) {
+    const uint32_t pk = pack_f16x2(v[I], v[I + 1]);
+    sts_u16_imm<I * 64>(d, (uint16_t)(pk & 0xffffu));
+    sts_u16_imm<(I + 1) * 64>(d, (uint16_t)(pk >> 16));
+    if constexpr (I + 2 < 32) WbStage<I + 2>::send(d, v);
+  }
+};
 __device__ __forceinline__ void math_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * 16) : "memory"); }
 
 // wait accounting (debug; make ALT=1 ALTFLAGS=-DSVB_WB_ACCOUNT, scripts/account_wbptt.py): cycles every role thread spends
@@ -406,17 +426,9 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         }
         if (WB_ABL(16)) {
         } else if (owner) {
-          const uint32_t d = src0 + buf * kWbOwnBytes + half * 32 * 128 + lane * 4;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sts_f32(d + i * 128, v[i]);
+          WbStage<0>::own(src0 + buf * kWbOwnBytes + half * 32 * 128 + lane * 4, v);
         } else {
-          const uint32_t d = src0 + buf * kWbSendBytes + half * 32 * 64 + lane * 2;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint32_t pk = pack_f16x2(v[i], v[i + 1]);
-            sts_u16(d + i * 64, (uint16_t)(pk & 0xffffu));
-            sts_u16(d + (i + 1) * 64, (uint16_t)(pk >> 16));
-          }
+          WbStage<0>::send(src0 + buf * kWbSendBytes + half * 32 * 64 + lane * 2, v);
         }
         if (!owner) {
           fence_proxy_async_smem();
