@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
   uint64_t* in_full = acc_empty + 2;           // [3] epilogue input tiles landed (tx)
   uint64_t* stg_full = in_full + 3;            // [3] 16 math warps: outputs staged (and c tiles read)
   uint64_t* stg_free = stg_full + 3;           // [3] store thread: in-place buffer reusable
-  uint64_t* recv_full = stg_free + 3;          // [2] 1 arming arrive + 12 KB of transactions: the peers' quarters landed
+  uint64_t* recv_full = stg_free + 3;          // [2] arming arrive + owner warp + 12 KB of transactions: all four quarters are here
   uint64_t* peer_free = recv_full + 2;         // [2] 3 remote arrives: my three receivers consumed (and re-armed) use k-1
   uint64_t* send_ready = peer_free + 2;        // [2] the owner exchange warp: own quarter staged
   uint64_t* consumed = send_ready + 2;         // [2] math thread 0: recv + own of this use are in registers
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 4);
-      mbar_init(&recv_full[b], 1);
+      mbar_init(&recv_full[b], 2);                // the arming arrive (+ 12 KB of transactions) and the owner exchange warp
       mbar_init(&peer_free[b], 3);
       mbar_init(&send_ready[b], 1);
       mbar_init(&consumed[b], 1);
@@ -438,9 +438,9 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
                             src0 + buf * kWbSendBytes + half * (kWbQuarterBytes / 2), kWbQuarterBytes / 2, rbar0 + buf * 8);
         }
       }
-      if (owner) {
+      if (owner) {                              // own quarter staged: counts into the same barrier as the three pushes
         __syncwarp();
-        if (lane == 0) mbar_arrive(&send_ready[buf]);
+        if (lane == 0) mbar_arrive(&recv_full[buf]);
       }
       if (owner) WL_STAMP(7); else WL_STAMP(2);
     }
@@ -486,10 +486,9 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
         } else if (is_R && t == T - 1 && j * kWbTile + row < p.B) {       // top layer, last frame: + dL/dh_last
           x0 = __ldg(reinterpret_cast<const float4*>(p.dh_last + (size_t)(j * kWbTile + row) * H + ns * 32) + ug);
         }
-        if (!WB_ABL(8192)) WB_ACC(1, mbar_wait_warp(&send_ready[buf], upar));
+        if (!WB_ABL(64)) WB_ACC(2, mbar_wait_warp(&recv_full[buf], upar));   // own quarter + the three received quarters
         const float4 o0 = lds_f4(own_a + buf * kWbOwnBytes + row * 128 + ug * 16);
         WL_STAMP(9);
-        if (!WB_ABL(64)) WB_ACC(2, mbar_wait_warp(&recv_full[buf], upar));
         dn[0] = o0.x; dn[1] = o0.y; dn[2] = o0.z; dn[3] = o0.w;
 #pragma unroll
         for (int sl = 0; sl < 3; ++sl) {
