@@ -85,6 +85,10 @@ int svb_set_persistent(int on);
  * one cooperative cluster launch, split-K over 4-CTA clusters with a DSMEM reduction) when H == 768 and L <= 3;
  * 0 = one fused GEMM + gate-backward launch per frame and batched dX GEMMs. */
 int svb_set_persistent_bwd(int on);
+/* Large-batch GE2E / get_cossim (rows x centroids >= 2^18, D % 64 == 0): 1 (default) = the three contractions run on
+ * tensor cores as 3-term split-fp16 products between the phase kernels, 0 = fp32 SIMT contractions (one cooperative
+ * launch).  Both agree with the float64 oracle to 1e-5 (utils.py:72-115,126-132). */
+int svb_set_ge2e_tensor_cores(int on);
 /* Weight gradients of the late frames beside the persistent BPTT kernel (csrc/lstm.cu): 1 (default; env
  * SVB_WGRAD_OVERLAP=0 disables) = the products dW = dG^T X over the last `pct` percent of the frames run on a
  * library-owned second stream, gated by the BPTT kernel's release counters, on the SMs it leaves idle; 0 = all

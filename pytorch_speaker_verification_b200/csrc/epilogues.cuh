@@ -19,6 +19,7 @@ struct EpiStoreF32 {
     int unpack_H;        // > 0: row m is a packed gate row (see lstm.cu); store to row gate*H + unit (direct path)
     int use_tma;
     int64_t z_stride;    // elements between the outputs of consecutive blockIdx.z slices (split-K partials, direct path)
+    int tma_z;           // TMA path: the map is [kz][M][N] and slice blockIdx.z stores into slab blockIdx.z
   };
   static constexpr int kInBytes = 0;
   static constexpr int kOutBytes = (BN / 32) * 16384;
@@ -49,7 +50,7 @@ struct EpiStoreF32 {
     if (!p.use_tma) return;
 #pragma unroll
     for (int c = 0; c < BN / 32; ++c)
-      if (n0 + c * 32 < p.N) tma_store_3d(&p.tc, out + c * 16384, n0 + c * 32, m0, 0);
+      if (n0 + c * 32 < p.N) tma_store_3d(&p.tc, out + c * 16384, n0 + c * 32, m0, p.tma_z ? (int)blockIdx.z : 0);
   }
 };
 

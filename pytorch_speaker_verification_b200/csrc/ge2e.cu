@@ -13,6 +13,9 @@
 //   C  per (8 centroids x 32 dims): dC_k = (sum_rows A_off e^ - q_k c^_k)/|c_k|
 //   D  per speaker : dE += dC_j/M + leave-one-out chain; block 0 reduces loss, dw, db deterministically
 // Reductions are warp shuffles + fixed-order shared-memory trees (no float atomics -> run-to-run identical).
+#include <cuda_fp16.h>
+#include "tc_gemm.cuh"
+#include "epilogues.cuh"
 #include "../../include/svb200.h"
 #include "perdev.cuh"
 #include <cooperative_groups.h>
@@ -25,6 +28,7 @@ namespace cg = cooperative_groups;
 
 namespace svb {
 void set_error(const char* what, cudaError_t e);
+int make_operand_map(CUtensorMap* out, const void* p, int rows, int K, int64_t ld, int mn_major, int box_rows_kmajor);
 
 constexpr float kCosEps = 1e-8f;    // F.cosine_similarity eps (utils.py:91,105)
 constexpr float kCosBias = 1e-6f;   // utils.py:114
@@ -65,10 +69,19 @@ struct Ge2eArgs {
   float* rowstat;        // [3, N*M]: per-row loss, dw, db contributions
   float* dC;             // [Nc, D]  P = A_off^T E^ (numerator of the centroid gradient)
   float* R;              // [N*M, D] A_off C^
+  // tensor-core path (large batches): fp16 hi / lo splits of E^, C^ and A_off (x = hi + lo to 22 bits), or null
+  __half *Eh, *El;       // [N*M, D]
+  __half *Ch, *Cl;       // [Nc, D]
+  __half *Ah, *Al;       // [N*M, Nc]
   long long* trace;      // debug (SVB_GE2E_TRACE=1): [N, 16] clock64 stamps of the per-speaker kernel, else null
   unsigned* bar;         // per-speaker kernel, cluster form: the word of its own grid barrier
 };
 
+// x = hi + lo with two IEEE halves: 22 significant bits (|x| <= 65504; lo underflows below 6e-8 absolute)
+__device__ __forceinline__ void split_h2(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -116,7 +129,11 @@ __device__ void phase_a(const Ge2eArgs& a, float* smem) {
     if (!a.Cext) {
       cc = block_sum(cc, red);
       const float inc = 1.0f / fmaxf(sqrtf(cc), kCosEps);
-      for (int d = threadIdx.x; d < D; d += kThreads) a.Chat[(size_t)j * D + d] = s[d] * invM * inc;
+      for (int d = threadIdx.x; d < D; d += kThreads) {
+        const float c = s[d] * invM * inc;
+        a.Chat[(size_t)j * D + d] = c;
+        if (a.Ch) split_h2(c, a.Ch[(size_t)j * D + d], a.Cl[(size_t)j * D + d]);
+      }
       if (threadIdx.x == 0) a.inv_nc[j] = inc;
     }
     __syncthreads();
@@ -132,7 +149,11 @@ __device__ void phase_a(const Ge2eArgs& a, float* smem) {
       const float ine = 1.0f / fmaxf(sqrtf(ee), kCosEps);
       const float inu = 1.0f / fmaxf(sqrtf(uu), kCosEps);
       const size_t row = (size_t)j * M + m;
-      for (int d = lane; d < D; d += 32) a.Ehat[row * D + d] = e[d] * ine;
+      for (int d = lane; d < D; d += 32) {
+        const float x = e[d] * ine;
+        a.Ehat[row * D + d] = x;
+        if (a.Eh) split_h2(x, a.Eh[row * D + d], a.El[row * D + d]);
+      }
       if (lane == 0) {
         a.inv_ne[row] = ine;
         a.inv_nu[row] = inu;
@@ -148,7 +169,11 @@ __device__ void phase_a(const Ge2eArgs& a, float* smem) {
       for (int d = lane; d < a.D; d += 32) cc += c[d] * c[d];
       cc = warp_sum(cc);
       const float inc = 1.0f / fmaxf(sqrtf(cc), kCosEps);
-      for (int d = lane; d < a.D; d += 32) a.Chat[(size_t)k * a.D + d] = c[d] * inc;
+      for (int d = lane; d < a.D; d += 32) {
+        const float x = c[d] * inc;
+        a.Chat[(size_t)k * a.D + d] = x;
+        if (a.Ch) split_h2(x, a.Ch[(size_t)k * a.D + d], a.Cl[(size_t)k * a.D + d]);
+      }
       if (lane == 0) a.inv_nc[k] = inc;
     }
   }
@@ -269,7 +294,9 @@ __device__ void phase_b2(const Ge2eArgs& a) {
         dwp += g * (c0 + kCosBias);
         const float A = w * g;
         if (k == j) ad = A;
-        a.Aoff[(size_t)row * Nc + k] = (k == j) ? 0.f : A;
+        const float ao = (k == j) ? 0.f : A;
+        if (a.Ah) split_h2(ao, a.Ah[(size_t)row * Nc + k], a.Al[(size_t)row * Nc + k]);
+        else a.Aoff[(size_t)row * Nc + k] = ao;
       }
       dwp = warp_sum(dwp); ad = warp_sum(ad);
       if (lane == 0) {
@@ -317,9 +344,17 @@ __device__ void phase_c(const Ge2eArgs& a, float* smem) {
 // ---------------------------------------------------------------------------------------------- phase D
 // per speaker j: dC_j = (P_j - (P_j.c^_j) c^_j)/|c_j|;  per row: r = R.e^ (= sum_k A_off cos, since cos = e^.c^);
 // dE = (R - r e^)/|e| + a (u^ - cosd e^)/|e| + dC_j/M + (sum_m dU_m - dU_i)/(M-1)
+// fixed order (deterministic); the loads of four slices are in flight together (one dependent L2 round trip per slice
+// made phase D the longest kernel of the tensor-core path: 16 slices x ~0.6 us)
 __device__ float sum_slices(const float* p, size_t stride, int n) {
   float v = 0.f;
-  for (int i = 0; i < n; ++i) v += p[(size_t)i * stride];
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const float x0 = p[(size_t)i * stride], x1 = p[(size_t)(i + 1) * stride], x2 = p[(size_t)(i + 2) * stride],
+                x3 = p[(size_t)(i + 3) * stride];
+    v += x0; v += x1; v += x2; v += x3;
+  }
+  for (; i < n; ++i) v += p[(size_t)i * stride];
   return v;
 }
 __device__ void phase_d(const Ge2eArgs& a, float* smem) {
@@ -425,12 +460,15 @@ __global__ void __launch_bounds__(kThreads) ge2e_fused_kernel(const Ge2eArgs a) 
   grid.sync();
   phase_d(a, smem);
 }
-__global__ void __launch_bounds__(kThreads) ge2e_phase_kernel(const Ge2eArgs a, int phase) {
+// One kernel per phase (multi-launch forms): each phase gets its own register allocation and occupancy (as one kernel
+// with a run-time phase switch every phase ran at the 164 registers of the widest one: one CTA per SM).
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads) ge2e_phase_kernel(const Ge2eArgs a) {
   extern __shared__ float smem[];
-  if (phase == 0) phase_a(a, smem);
-  else if (phase == 1) phase_b1(a, smem);
-  else if (phase == 2) phase_b2(a);
-  else if (phase == 3) phase_c(a, smem);
+  if (PHASE == 0) phase_a(a, smem);
+  else if (PHASE == 1) phase_b1(a, smem);
+  else if (PHASE == 2) phase_b2(a);
+  else if (PHASE == 3) phase_c(a, smem);
   else phase_d(a, smem);
 }
 
@@ -861,6 +899,9 @@ static size_t carve(Ge2eArgs& a, char* base) {
   a.Ehat = take(NM * D); a.Chat = take(Nc * D); a.Ssum = take((size_t)a.N * D);
   a.inv_ne = take(NM); a.inv_nu = take(NM); a.cosd = take(NM); a.inv_nc = take(Nc);
   a.cosm = take(NM * Nc); a.Aoff = take(NM * Nc); a.adiag = take(NM); a.rowstat = take(3 * NM); a.dC = take((size_t)(spk_candidate(a.N, a.M, a.D, a.Nc) && a.N > a.psplit ? a.N : a.psplit) * Nc * D); a.R = take(NM * D);
+  auto take_h = [&](size_t nhalfs) { return reinterpret_cast<__half*>(take((nhalfs + 1) / 2)); };
+  a.Eh = take_h(NM * D); a.El = take_h(NM * D); a.Ch = take_h(Nc * D); a.Cl = take_h(Nc * D);
+  a.Ah = take_h(NM * Nc); a.Al = take_h(NM * Nc);
   a.trace = reinterpret_cast<long long*>(take(2 * 16 * (size_t)kSpkMaxN));
   return off;
 }
@@ -896,6 +937,10 @@ extern "C" int svb_ge2e_trace_offset(int N, int M, int D, int Nc, size_t* offset
   return SVB_OK;
 }
 
+// tensor-core path of the large-batch GE2E: 1 (default; env SVB_GE2E_TC=0 clears it) or 0 = fp32 SIMT contractions only
+static int g_ge2e_tc = (getenv("SVB_GE2E_TC") != nullptr && atoi(getenv("SVB_GE2E_TC")) == 0) ? 0 : 1;
+extern "C" int svb_set_ge2e_tensor_cores(int on) { g_ge2e_tc = on != 0; return SVB_OK; }
+
 static int ge2e_impl(const float* E, const float* Cext, int N, int M, int D, int Nc, int col0, const float* w,
                      const float* b, const float* dcos, const float* gscale, float* cos_out, float* per_out,
                      float* loss_out, float* dE, float* dCext, float* dw, float* db, void* workspace,
@@ -922,7 +967,11 @@ static int ge2e_impl(const float* E, const float* Cext, int N, int M, int D, int
   const int num_sms = device_sm_count();
   if ((int)smem > max_smem_set) {
     cudaError_t e = cudaFuncSetAttribute(ge2e_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ge2e_phase_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("svb_ge2e: cudaFuncSetAttribute", e); return SVB_ERR_CUDA; }
     max_smem_set = (int)smem;
   }
@@ -1000,6 +1049,80 @@ static int ge2e_impl(const float* E, const float* Cext, int N, int M, int D, int
       cluster_ok = 0;
     }
   }
+  // ---- tensor-core path for large batches (C3: N = 512, the C5 similarity matrix): the three contractions
+  //      cos = E^ C^T, R = A_off C^, P = A_off^T E^ run on tcgen05 as 3-term split-fp16 products
+  //      (hi hi + hi lo + lo hi: ~2^-22, inside the 1e-5 tolerance where bf16 would not be) between the phase kernels.
+  //      The SIMT GEMM phases are 95 % of the fused kernel's 205 us at N = 512.
+  const bool tc_off = g_ge2e_tc == 0;
+  static const size_t tc_min = getenv("SVB_GE2E_TC_MIN") ? (size_t)atoll(getenv("SVB_GE2E_TC_MIN")) : ((size_t)1 << 18);
+  const bool tc_path = !tc_off && !dcos && D % 64 == 0 && Nc % 8 == 0 && NMr >= 512 && Nc >= 128 &&
+                       (size_t)NMr * Nc >= tc_min;
+  if (tc_path) {
+    auto gemm3 = [&](const __half* A0, const __half* A1, int a_rows, int64_t lda, int a_mn, const __half* B0, const __half* B1,
+                     int b_rows, int64_t ldb, int b_mn, float* C, int Mo, int No, int K, int kz) -> int {
+      GemmOperands g;
+      memset(&g, 0, sizeof(g));
+      g.nterms = 3; g.f16 = 1; g.M = Mo; g.N = No; g.K = K; g.kz = kz > 1 ? kz : 0;
+      const __half* As[3] = {A0, A0, A1};
+      const __half* Bs[3] = {B0, B1, B0};
+      // the maps always describe the WHOLE reduction (kz slices address it by blockIdx.z; rows past the end are zero-filled)
+      const int Ktot = a_mn ? a_rows : K;
+      for (int t = 0; t < 3; ++t) {
+        int e = make_operand_map(&g.ta[t], As[t], Mo, Ktot, lda, a_mn, kBM);
+        if (e) return e;
+        e = make_operand_map(&g.tb[t], Bs[t], No, Ktot, ldb, b_mn, 128);
+        if (e) return e;
+      }
+      (void)b_rows;
+      if (!a_mn && !b_mn && No % 256 == 0 && kz <= 1) {
+        // wide output (cos = E^ C^T at N = 512: 40 x 2 tiles of 128 x 256 fill the machine in ONE wave; 128 x 128 tiles
+        // are 160 CTAs = two waves for 148 SMs)
+        EpiStoreF32<256>::Params ep2;
+        int e2 = make_store_params<256>(&ep2, C, nullptr, Mo, No, (int64_t)No, 0);
+        if (e2) return e2;
+        if (ep2.use_tma) {
+          for (int t = 0; t < 3; ++t) {
+            e2 = make_operand_map(&g.tb[t], Bs[t], No, Ktot, ldb, 0, 256);
+            if (e2) return e2;
+          }
+          cudaError_t ce2 = launch_tc_gemm<256, 4, false, false, EpiStoreF32<256>, 8>(g, ep2, s);
+          if (ce2 != cudaSuccess) { set_error("svb_ge2e: tensor-core GEMM (128 x 256 tiles)", ce2); return SVB_ERR_CUDA; }
+          return SVB_OK;
+        }
+      }
+      EpiStoreF32<128>::Params ep;
+      int e = make_store_params<128>(&ep, C, nullptr, Mo, No, (int64_t)No, 0);
+      if (e) return e;
+      if (!ep.use_tma) { set_error("svb_ge2e: tensor-core path needs 16-byte aligned outputs", cudaSuccess); return SVB_ERR_ARG; }
+      if (kz > 1) {
+        e = make_tmap(&ep.tc, C, 4, (uint64_t)No, (uint64_t)Mo, (uint64_t)kz, (uint64_t)No, (uint64_t)No * Mo, 32, 128, 3);
+        if (e) return e;
+        ep.tma_z = 1;
+      }
+      cudaError_t ce;
+      if (!a_mn && !b_mn) ce = launch_tc_gemm<128, 4, false, false, EpiStoreF32<128>>(g, ep, s);
+      else if (!a_mn && b_mn) ce = launch_tc_gemm<128, 4, false, true, EpiStoreF32<128>>(g, ep, s);
+      else ce = launch_tc_gemm<128, 4, true, true, EpiStoreF32<128>>(g, ep, s);
+      if (ce != cudaSuccess) { set_error("svb_ge2e: tensor-core GEMM", ce); return SVB_ERR_CUDA; }
+      return SVB_OK;
+    };
+    ge2e_phase_kernel<0><<<N < 4 * num_sms ? N : 4 * num_sms, kThreads, smem, s>>>(a);
+    int e = gemm3(a.Eh, a.El, NMr, D, 0, a.Ch, a.Cl, Nc, D, 0, a.cosm, NMr, Nc, D, 1);               // cos = E^ C^T
+    if (e) return e;
+    ge2e_phase_kernel<2><<<b2blocks, kThreads, 0, s>>>(a);
+    if (a.need_grad) {
+      e = gemm3(a.Ah, a.Al, NMr, Nc, 0, a.Ch, a.Cl, D, D, 1, a.R, NMr, D, Nc, 1);                   // R = A_off C^
+      if (e) return e;
+      // P = A_off^T E^ over psplit slices of prows rows (phase D adds the slices in order)
+      e = gemm3(a.Ah, a.Al, NMr, Nc, 1, a.Eh, a.El, D, D, 1, a.dC, Nc, D, a.prows, a.psplit);
+      if (e) return e;
+    }
+    ge2e_phase_kernel<4><<<N < 4 * num_sms ? N : 4 * num_sms, kThreads, smem, s>>>(a);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { set_error("svb_ge2e: launch (tensor-core path)", ce); return SVB_ERR_CUDA; }
+    return SVB_OK;
+  }
+  a.Eh = a.El = a.Ch = a.Cl = a.Ah = a.Al = nullptr;      // (the fp32 paths do not write the splits)
   if (fused) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ge2e_fused_kernel, kThreads, smem);
@@ -1010,11 +1133,11 @@ static int ge2e_impl(const float* E, const float* Cext, int N, int M, int D, int
     cudaError_t e = cudaLaunchCooperativeKernel((void*)ge2e_fused_kernel, dim3(grid), dim3(kThreads), params, smem, s);
     if (e != cudaSuccess) { set_error("svb_ge2e: cooperative launch", e); return SVB_ERR_CUDA; }
   } else {
-    ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 0);
-    ge2e_phase_kernel<<<b1tiles, kThreads, smem, s>>>(a, 1);
-    ge2e_phase_kernel<<<b2blocks, kThreads, smem, s>>>(a, 2);
-    if (a.need_grad) ge2e_phase_kernel<<<ctiles, kThreads, smem, s>>>(a, 3);
-    ge2e_phase_kernel<<<N, kThreads, smem, s>>>(a, 4);
+    ge2e_phase_kernel<0><<<N, kThreads, smem, s>>>(a);
+    ge2e_phase_kernel<1><<<b1tiles, kThreads, smem, s>>>(a);
+    ge2e_phase_kernel<2><<<b2blocks, kThreads, smem, s>>>(a);
+    if (a.need_grad) ge2e_phase_kernel<3><<<ctiles, kThreads, smem, s>>>(a);
+    ge2e_phase_kernel<4><<<N, kThreads, smem, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("svb_ge2e: launch", e); return SVB_ERR_CUDA; }
   }

@@ -97,6 +97,12 @@ def set_persistent_bwd(on):
     check(_lib.lib().svb_set_persistent_bwd(int(bool(on))), "svb_set_persistent_bwd")
 
 
+def set_ge2e_tensor_cores(on):
+    """True (default): large GE2E / get_cossim problems run their three contractions on tensor cores (3-term split
+    fp16); False: the fp32 SIMT kernel."""
+    check(_lib.lib().svb_set_ge2e_tensor_cores(int(bool(on))), "svb_set_ge2e_tensor_cores")
+
+
 def set_wgrad_overlap(on):
     """True (default): the weight-gradient products over the late frames run on a second stream beside the persistent
     BPTT kernel (which leaves 28 SMs idle); False: all of them after it."""

@@ -104,6 +104,40 @@ def test_ge2e_speaker_kernel_matches_general_kernel(svb, shape):
         assert rel(crit(torch.tensor(Enp, device="cuda")).item(), o["loss"]) < 1e-5
 
 
+def test_ge2e_tensor_core_path_matches_fp32_path(svb):
+    """Large batches (rows x centroids >= 2^18) run cos = E^ C^T, R = A_off C^, P = A_off^T E^ as 3-term split-fp16
+    tcgen05 GEMMs between the phase kernels: same loss / dE / dw / db as the fp32 SIMT kernel and the float64 oracle
+    (utils.py:72-115,126-132), in the full-batch form, the row-sharded form (svb_ge2e_rows) and get_cossim."""
+    from pytorch_speaker_verification_b200 import ops
+    N, M, D = 320, 7, 256                                    # 2240 rows x 320 centroids: ragged 128-row tiles
+    r = np.random.RandomState(7)
+    Enp = (r.randn(N, 1, D) + 0.8 * r.randn(N, M, D)).astype(np.float32)
+    o = oge2e.ge2e_fwd_bwd(Enp.astype(np.float64), 10.0, -5.0)
+    out = {}
+    try:
+        for tc in (True, False):
+            ops.set_ge2e_tensor_cores(tc)
+            E = torch.tensor(Enp, device="cuda", requires_grad=True)
+            crit = svb.GE2ELoss("cuda")
+            loss = crit(E)
+            loss.backward()
+            assert rel(loss.item(), o["loss"]) < 1e-5, tc
+            assert rel(E.grad.cpu().numpy(), o["dE"]) < 1e-5, tc
+            assert rel(crit.w.grad.item(), o["dw"]) < 1e-5, tc
+            Cc = svb.get_centroids(E.detach())
+            red, dEr = torch.ops.svb200.ge2e_rows(E.detach()[:160].contiguous(), Cc, crit.w.detach(), crit.b.detach(), 0)
+            with torch.no_grad():
+                cos = svb.get_cossim(E.detach(), Cc)
+            out[tc] = (loss.item(), E.grad.clone(), red.clone(), dEr.clone(), cos.clone())
+    finally:
+        ops.set_ge2e_tensor_cores(True)
+    a, b = out[True], out[False]
+    assert rel(a[0], b[0]) < 1e-6
+    assert rel(a[1].cpu().numpy(), b[1].cpu().numpy()) < 1e-5
+    assert rel(a[2].cpu().numpy(), b[2].cpu().numpy()) < 1e-5 and rel(a[3].cpu().numpy(), b[3].cpu().numpy()) < 1e-5
+    assert float((a[4] - b[4]).abs().max()) < 2e-6
+
+
 def test_ge2e_upstream_scale_and_no_grad(svb):
     N, M, D, kind, w0, b0 = I.GE2E_CASES["c1"]
     Enp = I.ge2e_embeddings(N, M, D, kind)
