@@ -127,25 +127,11 @@ __device__ __forceinline__ int bucket_of64(float v, const float* thr) {
   return lo;
 }
 
-// ---- single-launch sweep: one warp per speaker (all its float4 loads issued up front), integer atomics into the
-// ---- global totals, and the last block to finish reproduces the reference's float32 arithmetic.
-__device__ __forceinline__ void eer_scan(const float* far_s, const float* frr_s, int T, float* out) {
-  float diff = 1.0f, EER = 0.f, eFAR = 0.f, eFRR = 0.f;
-  int sel = -1;
-  for (int k = 0; k < T; ++k) {
-    const float d = fabsf(__fsub_rn(far_s[k], frr_s[k]));
-    if (diff > d) {
-      diff = d;
-      EER = __fdiv_rn(__fadd_rn(far_s[k], frr_s[k]), 2.0f);
-      sel = k; eFAR = far_s[k]; eFRR = frr_s[k];
-    }
-  }
-  out[0] = EER; out[1] = (float)sel; out[2] = eFAR; out[3] = eFRR;
-}
-
+// ---- single-launch sweep: one CTA per speaker, integer atomics into the global totals, and the last block to finish
+// ---- reproduces the reference's float32 arithmetic.
 constexpr int kSweepWarps = 4;
 constexpr int kBk = 64;           // bucket rows of the lane-private histogram (T + 1 <= 64 on this path)
-// scratch (zeroed once by the host; the last block re-zeroes it): [0] block ticket, then 8 replicas of the totals [8][2][T]: sum over speakers of
+// scratch (zeroed once by the host; the last block re-zeroes it): [0] master ticket, then 7 replicas of the totals [7][2][T] and 2T words of group tickets: sum over speakers of
 // (cnt_all - cnt_diag) and of cnt_diag, accumulated with integer atomics (exact in any order).
 // One CTA (4 warps) per speaker: each warp takes a quarter of the speaker's (Mv x N) row block.
 __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float* __restrict__ sim, int N, int Mv, int Nc,
@@ -235,13 +221,28 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
     const int sd = t + 1 < kBk ? suf_diag[t + 1] : 0;
     cnt_all[(size_t)i * T + t] = sa;
     cnt_diag[(size_t)i * T + t] = sd;
-    unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x & 7) * 2 * T;
+    unsigned long long* part = scratch + 1 + (size_t)(blockIdx.x % 7) * 2 * T;
     if (sa - sd) atomicAdd(&part[t], (unsigned long long)(sa - sd));
     if (sd) atomicAdd(&part[T + t], (unsigned long long)sd);
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(&scratch[0], 1ULL) == gridDim.x - 1) ? 1 : 0;
+  // Two-level block ticket: gridDim.x returning atomics on ONE word serialise in L2 (1024 of them were a large part of
+  // the kernel's 5.5 us tail); the blocks take a ticket in one of G groups (the words of the unused 8th replica), the
+  // last block of a group takes the master ticket.
+  if (threadIdx.x == 0) {
+    const unsigned G = 2u * T < 32u ? 2u * T : 32u;
+    const unsigned g = blockIdx.x % G;
+    const unsigned in_group = (gridDim.x - g + G - 1) / G;              // blocks b with b % G == g
+    unsigned long long* grp = scratch + 1 + (size_t)7 * 2 * T;
+    int l = 0;
+    if (atomicAdd(&grp[g], 1ULL) == in_group - 1) {
+      __threadfence();
+      const unsigned groups = gridDim.x < G ? gridDim.x : G;
+      l = (atomicAdd(&scratch[0], 1ULL) == groups - 1) ? 1 : 0;
+    }
+    last = l;
+  }
   __syncthreads();
   if (!last) return;
   __threadfence();
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     unsigned long long fa = 0, di = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < 7; ++r) {
       fa += __ldcg(scratch + 1 + (size_t)r * 2 * T + t);
       di += __ldcg(scratch + 1 + (size_t)r * 2 * T + T + t);
     }
@@ -264,8 +265,35 @@ __global__ void __launch_bounds__(32 * kSweepWarps) eer_sweep_kernel(const float
   }
   const int all_exact = __syncthreads_and(exact ? 1 : 0);
   for (int t = threadIdx.x; t < 1 + 16 * T; t += blockDim.x) scratch[t] = 0;   // self-cleaning: ready for the next call
+  // The reference's strict "diff > |FAR - FRR|" scan from diff = 1 selects the FIRST index of the minimum (if it is
+  // below 1): a parallel arg-min with ties to the lower index instead of 50 dependent steps.  T < 64: warps 0 and 1.
+  __shared__ float wmin[2];
+  __shared__ int wsel[2];
+  if (warp < 2) {
+    const int t = threadIdx.x;
+    float d = INFINITY;
+    int sel = -1;
+    if (t < T) {
+      const float dd = fabsf(__fsub_rn(far_s[t], frr_s[t]));
+      if (1.0f > dd) { d = dd; sel = t; }               // (NaN is never selected)
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int os = __shfl_xor_sync(0xffffffffu, sel, o);
+      if (os >= 0 && (sel < 0 || od < d || (od == d && os < sel))) { d = od; sel = os; }
+    }
+    if (lane == 0) { wmin[warp] = d; wsel[warp] = sel; }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    eer_scan(far_s, frr_s, T, out);
+    const int sel = wsel[0] >= 0 && (wsel[1] < 0 || wmin[0] <= wmin[1]) ? wsel[0] : wsel[1];
+    if (sel >= 0) {
+      out[0] = __fdiv_rn(__fadd_rn(far_s[sel], frr_s[sel]), 2.0f);
+      out[1] = (float)sel; out[2] = far_s[sel]; out[3] = frr_s[sel];
+    } else {
+      out[0] = 0.f; out[1] = -1.0f; out[2] = 0.f; out[3] = 0.f;
+    }
     if (!all_exact) out[1] = -2.0f;                     // caller falls back to the sequential float32 kernel
   }
 }
