@@ -32,7 +32,11 @@ constexpr int kWbKbPerStage = 3;       // 12 MMAs per barrier wait
 constexpr int kWbStages = 3;           // ring: 3 x 24 KB (a tile is 4 stages; 5 x 16 KB measured 5 % slower)
 constexpr int kWbStageBytes = kWbKbPerStage * kWbTile * 128;
 constexpr int kWbXRing = 3;
+#ifdef SVB_WB_DEPS
+constexpr int kWbDeps = SVB_WB_DEPS;   // (experiment: make ALT=1 ALTFLAGS=-DSVB_WB_DEPS=16)
+#else
 constexpr int kWbDeps = 8;             // dependency slots: the poller runs up to 8 tiles ahead of the slowest waiter
+#endif
 // Warp roles.  Every single-thread role has a warp of its own: two roles in one warp run time-sliced, and a lane that
 // sleeps in mbarrier.try_wait holds the other one up (poller and input loader shared a warp at first: the TMA producer
 // then waited 1200 cycles per tile for dependencies that had been satisfied long before).  The single-thread roles sit
