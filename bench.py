@@ -509,7 +509,12 @@ def main():
     net = svb.SpeechEmbedder().to(dev)
     net.recurrent_terms = args.recurrent_terms
     crit = svb.GE2ELoss(dev)
-    loss_mod = GlobalGE2ELoss(crit) if world > 1 else crit
+    # GE2E exchange of the N-rank step: "rows" (default) = NCCL all-gather of the centroids + all-reduce of their
+    # gradients; "peer" = the same two steps as plain loads over NVLink peer memory (symmetric buffers, two device-side
+    # barriers, no NCCL call).  Measured equal at 2 GPUs (9.51-9.59 vs 9.55-9.70 ms/step: the exchange is ~0.15 ms of
+    # launch latencies either way), so the default stays the one with fewer launches; SVB_GE2E_EXCHANGE selects.
+    ge2e_exchange = os.environ.get("SVB_GE2E_EXCHANGE", "rows")
+    loss_mod = GlobalGE2ELoss(crit, mode=ge2e_exchange) if world > 1 else crit
     params = list(net.parameters())
     opt = torch.optim.SGD([{'params': net.parameters()}, {'params': crit.parameters()}], lr=0.01)
     B = N_SPK * M_UTT

@@ -89,6 +89,18 @@ int svb_set_persistent_bwd(int on);
  * tensor cores as 3-term split-fp16 products between the phase kernels, 0 = fp32 SIMT contractions (one cooperative
  * launch).  Both agree with the float64 oracle to 1e-5 (utils.py:72-115,126-132). */
 int svb_set_ge2e_tensor_cores(int on);
+
+/* ---- multi-GPU GE2E exchange over NVLink peer memory (new: the reference, speech_embedder_net.py:43-49, is
+ * single-device).  `peer_ptrs_dev` is a DEVICE array of `world` float pointers: the same symmetric buffer on every rank
+ * (torch.distributed._symmetric_memory: handle.buffer_ptrs_dev).  The caller separates writes and reads of the buffers
+ * with the handle's barrier.  Sums are taken in rank order (identical on every rank).
+ *   svb_peer_gather: out[r * n + i] = peer_r[offset + i]                      (centroid all-gather)
+ *   svb_peer_reduce: seg_out[i] = sum_r peer_r[offset + seg_offset + i], tail_out[k] = sum_r peer_r[offset + tail_offset + k]
+ *                    (this rank's rows of the centroid gradient + the loss / dw / db scalars)
+ * Lengths and offsets in floats, multiples of 4 except the tail (<= 256 floats). */
+int svb_peer_gather(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t n_floats, float* out, void* stream);
+int svb_peer_reduce(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t seg_offset, size_t seg_floats,
+                    size_t tail_offset, int tail_floats, float* seg_out, float* tail_out, void* stream);
 /* Weight gradients of the late frames beside the persistent BPTT kernel (csrc/lstm.cu): 1 (default; env
  * SVB_WGRAD_OVERLAP=0 disables) = the products dW = dG^T X over the last `pct` percent of the frames run on a
  * library-owned second stream, gated by the BPTT kernel's release counters, on the SMs it leaves idle; 0 = all

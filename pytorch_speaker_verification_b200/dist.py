@@ -86,25 +86,106 @@ class _ShardedGE2EFn(torch.autograd.Function):
     backward = _GlobalGE2EFn.backward
 
 
+class PeerExchange:
+    """Symmetric buffers of one process group for the GE2E exchange over NVLink peer memory
+    (torch.distributed._symmetric_memory): every rank writes its centroids / its centroid-gradient partials into ITS
+    buffer and reads the peers' buffers with plain loads (svb_peer_gather / svb_peer_reduce), two device-side barriers
+    per step instead of two NCCL collectives.  Layout per rank (floats): [own centroids N_local*D (padded to 4) |
+    dC partial Nc*D | loss, dw, db]."""
+
+    def __init__(self, group, n_local, D, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_local, self.D = int(n_local), int(D)
+        self.nc = self.world * self.n_local
+        self.off_c = 0
+        self.len_c = (self.n_local * self.D + 3) // 4 * 4
+        self.off_red = self.len_c
+        self.len_red = self.nc * self.D + 3
+        self.buf = symm.empty(self.len_c + (self.len_red + 3) // 4 * 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = int(self.handle.buffer_ptrs_dev)
+        torch.cuda.synchronize(device)
+        self.handle.barrier(channel=0)
+
+    def matches(self, n_local, D, device):
+        return self.n_local == int(n_local) and self.D == int(D) and self.buf.device == device
+
+
+class _PeerGE2EFn(torch.autograd.Function):
+    """Design "A" with the exchange over peer memory: same arithmetic as _ShardedGE2EFn, no NCCL call on the GE2E path."""
+
+    @staticmethod
+    def forward(ctx, local_emb, w, b, px):
+        Nl, M, D = local_emb.shape
+        E = local_emb.contiguous()
+        N = px.nc
+        px.buf[:Nl * D].view(Nl, D).copy_(torch.ops.svb200.centroids(E))
+        px.handle.barrier(channel=0)                       # every rank's centroids are in its buffer
+        C_all = torch.ops.svb200.peer_gather(px.buf, px.ptrs, px.world, px.off_c, px.len_c)[:, :Nl * D].reshape(N, D)
+        red, dE = torch.ops.svb200.ge2e_rows(E, C_all.contiguous(), w.detach(), b.detach(), px.rank * Nl)
+        px.buf[px.off_red:px.off_red + px.len_red].copy_(red)
+        px.handle.barrier(channel=1)                       # every rank's partials are in its buffer
+        dC_own, tail = torch.ops.svb200.peer_reduce(px.buf, px.ptrs, px.world, px.off_red, px.rank * Nl * D, Nl * D,
+                                                    N * D, 3)
+        dE = dE + torch.ops.svb200.centroids_bwd(dC_own.view(Nl, D), M)
+        ctx.save_for_backward(dE, tail[1].clone(), tail[2].clone())
+        return tail[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        dE, dw, db = ctx.saved_tensors
+        dE, dw, db = torch.ops.svb200.scale3(dE, dw, db, g)
+        return dE, dw, db, None
+
+
+
+
 class GlobalGE2ELoss(torch.nn.Module):
     """Wraps a GE2ELoss so that ``forward(local_embeddings (N_local, M, D))`` returns the loss of the GLOBAL batch
     (the same number on every rank) and back-propagates this rank's slice of dL/dE.
 
     ``mode="rows"`` (default): centroid all-gather + this rank's rows against all centroids + one all-reduce of the
-    centroid gradients (design A); ``mode="gather"``: d-vector all-gather, every rank evaluates the global batch
+    centroid gradients (design A); ``mode="peer"``: the same with both exchange steps over NVLink peer memory
+    (symmetric buffers, svb_peer_gather / svb_peer_reduce, no NCCL call on the GE2E path; falls back to "rows" where
+    symmetric memory is unavailable); ``mode="gather"``: d-vector all-gather, every rank evaluates the global batch
     (design B, round 1).  ``compute`` injects the arithmetic (host-logic tests on CPU / gloo)."""
 
     def __init__(self, criterion, group=None, compute=None, mode="rows"):
         super().__init__()
-        if mode not in ("rows", "gather"):
+        if mode not in ("rows", "gather", "peer"):
             raise ValueError(mode)
         self.criterion = criterion
         self.group = group
         self.mode = mode
-        self.compute = compute or (_rows_loss_and_grads if mode == "rows" else _fused_loss_and_grads)
+        self.compute = compute or (_fused_loss_and_grads if mode == "gather" else _rows_loss_and_grads)
+        self._px = None
+
+    def _peer(self, E):
+        """The symmetric buffers of this (group, shape), or None when peer memory is not available (-> NCCL rows)."""
+        if self._px is False:
+            return None
+        Nl, _, D = E.shape
+        if self._px is None or not self._px.matches(Nl, D, E.device):
+            try:
+                if (Nl * D) % 4:
+                    raise RuntimeError("N_local * D must be a multiple of 4")
+                self._px = PeerExchange(self.group, Nl, D, E.device)
+            except Exception as exc:                    # no symmetric memory on this system / build
+                import warnings
+                warnings.warn(f"GlobalGE2ELoss(mode='peer'): falling back to the NCCL exchange ({exc!r})")
+                self._px = False
+                return None
+        return self._px
 
     def forward(self, local_embeddings):
-        fn = _ShardedGE2EFn if self.mode == "rows" else _GlobalGE2EFn
+        if self.mode == "peer" and local_embeddings.is_cuda:
+            px = self._peer(local_embeddings)
+            if px is not None:
+                return _PeerGE2EFn.apply(local_embeddings, self.criterion.w, self.criterion.b, px)
+        fn = _GlobalGE2EFn if self.mode == "gather" else _ShardedGE2EFn
         return fn.apply(local_embeddings, self.criterion.w, self.criterion.b, self.group, self.compute)
 
 

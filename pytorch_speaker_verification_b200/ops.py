@@ -400,6 +400,37 @@ def _ge2e_rows_fake(E, C, w, b, col0):
 _op("ge2e_rows(Tensor E, Tensor C, Tensor w, Tensor b, int col0) -> (Tensor, Tensor)", _ge2e_rows, _ge2e_rows_fake)
 
 
+def _peer_gather(anchor: torch.Tensor, peer_ptrs_dev: int, world: int, offset: int, n: int) -> torch.Tensor:
+    """out[r, i] = peer_r[offset + i]: `anchor` is this rank's symmetric buffer (device / stream of the launch)."""
+    out = torch.empty(int(world), int(n), dtype=torch.float32, device=anchor.device)
+    with torch.cuda.device(anchor.device):
+        check(_lib.lib().svb_peer_gather(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(int(offset)), _sz(int(n)),
+                                         ptr(out), stream_ptr(anchor.device)), "svb_peer_gather")
+    return out
+
+
+_op("peer_gather(Tensor anchor, int peer_ptrs_dev, int world, int offset, int n) -> Tensor", _peer_gather,
+    lambda anchor, p, world, offset, n: anchor.new_empty(world, n))
+
+
+def _peer_reduce(anchor: torch.Tensor, peer_ptrs_dev: int, world: int, offset: int, seg_offset: int, seg_n: int,
+                 tail_offset: int, tail_n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(sum over the ranks of peer_r[offset + seg_offset : + seg_n], of peer_r[offset + tail_offset : + tail_n]), in
+    rank order."""
+    seg = torch.empty(int(seg_n), dtype=torch.float32, device=anchor.device)
+    tail = torch.empty(int(tail_n), dtype=torch.float32, device=anchor.device)
+    with torch.cuda.device(anchor.device):
+        check(_lib.lib().svb_peer_reduce(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(int(offset)),
+                                         _sz(int(seg_offset)), _sz(int(seg_n)), _sz(int(tail_offset)), int(tail_n),
+                                         ptr(seg), ptr(tail), stream_ptr(anchor.device)), "svb_peer_reduce")
+    return seg, tail
+
+
+_op("peer_reduce(Tensor anchor, int peer_ptrs_dev, int world, int offset, int seg_offset, int seg_n, int tail_offset, "
+    "int tail_n) -> (Tensor, Tensor)", _peer_reduce,
+    lambda anchor, p, world, offset, so, sn, to, tn: (anchor.new_empty(sn), anchor.new_empty(tn)))
+
+
 def _scale3(dE: torch.Tensor, dw: torch.Tensor, db: torch.Tensor, g: torch.Tensor
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     dE, dw, db = dE.clone(), dw.clone(), db.clone()
@@ -719,5 +750,5 @@ _op("logmel(Tensor y, Tensor window, Tensor twiddle, Tensor mel_w, int hop, int 
     lambda y, window, twiddle, mel_w, hop, w0, w1: y.new_empty(mel_w.shape[0], 1 + y.numel() // hop))
 
 OP_NAMES = ["pack_weights", "embedder_fwd", "embedder_bwd", "ge2e_loss", "ge2e_rows", "scale3", "centroids", "centroids_bwd",
-            "utterance_centroids", "cossim", "cossim_bwd", "calc_loss", "calc_loss_bwd", "eer_counts", "eer_sweep",
+            "utterance_centroids", "cossim", "cossim_bwd", "calc_loss", "calc_loss_bwd", "eer_counts", "eer_sweep", "peer_gather", "peer_reduce",
             "eer_finish", "dvector_windows", "segment_mean", "clip_sgd", "logmel"]

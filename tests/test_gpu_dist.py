@@ -57,6 +57,24 @@ def _worker(rank, world, port, out):
     # inside the gradient tolerance of DESIGN.md section 2 (1.2e-2), not bit for bit
     for p, r in zip(net.parameters(), first):
         assert float((p.grad - r).norm() / r.norm()) < 1.2e-2
+    # design A with both exchange steps over NVLink peer memory (symmetric buffers, no NCCL call on the GE2E path):
+    # the same loss and, since the sums are taken in rank order from the same partials, the same gradients as the NCCL
+    # form up to the summation order of the all-reduce
+    net.zero_grad()
+    crit.zero_grad()
+    emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
+    glp = GlobalGE2ELoss(crit, mode="peer")
+    lossP = glp(emb.reshape(hi - lo, M, -1))
+    lossP.backward()
+    allreduce_gradients(list(net.parameters()))
+    assert glp._px not in (None, False), "peer memory was not used"
+    assert abs(lossP.item() - loss.item()) < 1e-6 * abs(loss.item())
+    assert abs(crit.w.grad.item() - w_first.item()) < 1e-5 * abs(w_first.item())
+    for p, r in zip(net.parameters(), first):
+        assert float((p.grad - r).norm() / r.norm()) < 1.2e-2
+    for _ in range(3):                               # buffer reuse across steps (two barriers per step)
+        l2 = glp(emb.detach().reshape(hi - lo, M, -1))
+        assert abs(l2.item() - lossP.item()) < 1e-6 * abs(lossP.item())
     # the same step with the bucketed all-reduce started from inside backward: identical sums
     from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
     ref = first                                  # (same GE2E mode: the sums must be bit-identical)
