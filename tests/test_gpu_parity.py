@@ -933,3 +933,26 @@ def test_log_mel_front_end_matches_oracle(svb, net):
     S = svb.log_mel_spectrogram(0.1 * r.randn(24000).astype(np.float32))          # 151 frames -> 11 windows
     out = svb.extract_dvectors(net, [S.cpu().numpy()])
     assert out[0].shape[1] == 256 and out[0].shape[0] >= 1
+
+
+def test_train_step_is_bitwise_reproducible(svb):
+    """Persistent forward + BPTT (bulk-copy DSMEM exchange, software-pipelined reduce / gate loop) + weight gradients
+    beside BPTT + per-speaker GE2E: every hand-off is ordered by barriers and counters and every sum has a fixed order,
+    so repeated steps on the same batch agree bit for bit (a lost hand-off or a stale read would show here)."""
+    torch.manual_seed(0)
+    net = svb.SpeechEmbedder().cuda()
+    crit = svb.GE2ELoss("cuda")
+    for (N, M, T, reps) in ((64, 10, 160, 12), (13, 10, 41, 12), (3, 7, 90, 12)):
+        x = torch.tensor(I.logmel(N * M, T, seed=5)).cuda()
+        ref = None
+        for _ in range(reps):
+            net.zero_grad(set_to_none=True)
+            crit.zero_grad(set_to_none=True)
+            loss = crit(net(x).reshape(N, M, -1))
+            loss.backward()
+            g = torch.cat([p.grad.reshape(-1) for p in net.parameters()] + [crit.w.grad.reshape(1), loss.detach().reshape(1)])
+            assert torch.isfinite(g).all()
+            if ref is None:
+                ref = g.clone()
+            else:
+                assert torch.equal(g, ref), (N, M, T)
