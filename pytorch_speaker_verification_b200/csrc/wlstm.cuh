@@ -188,6 +188,19 @@ __device__ __forceinline__ void wl_advance(int& t, int& j, int& jc, int& je, int
   }
 }
 
+template <int kOff> __device__ __forceinline__ void wl_sts_u16_imm(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(addr), "h"(v), "n"(kOff) : "memory");
+}
+// gate stash of one 16-row part: rows I, I + 1 of the thread's gate column, 128B-swizzled rows of 128 bytes
+template <int I, int kBase> struct WlStash {
+  static __device__ __forceinline__ void run(uint32_t gbase0, const float (&a)[16]) {
+    const uint32_t pk = pack_f16x2(a[I], a[I + 1]);
+    wl_sts_u16_imm<kBase + I * 128>(gbase0 ^ ((I & 7) << 4), (uint16_t)(pk & 0xffffu));
+    wl_sts_u16_imm<kBase + (I + 1) * 128>(gbase0 ^ (((I + 1) & 7) << 4), (uint16_t)(pk >> 16));
+    if constexpr (I + 2 < 16) WlStash<I + 2, kBase>::run(gbase0, a);
+  }
+};
+
 template <int H>
 __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_constant__ WlstmParams p) {
   constexpr int NS = H / 32;                 // gate-column slices per layer
@@ -539,12 +552,8 @@ __global__ void __launch_bounds__(kWlThreads, 1) wlstm_fwd_kernel(const __grid_c
         if (p.ablate & 2) continue;
         if (p.training) {
           // gate stash [row][packed col] fp16 (see pack8_stash): two boxes of 64 columns, 128B-swizzled rows
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const uint32_t pk = pack_f16x2(a[i], a[i + 1]);
-            sts_u16((gbase0 ^ ((i & 7) << 4)) + ps * 4096 + i * 128, (uint16_t)(pk & 0xffffu));
-            sts_u16((gbase0 ^ (((i + 1) & 7) << 4)) + ps * 4096 + (i + 1) * 128, (uint16_t)(pk >> 16));
-          }
+          // (offsets as immediates: one XOR per store instead of XOR + two adds)
+          if (ps == 0) WlStash<0, 0>::run(gbase0, a); else WlStash<0, 4096>::run(gbase0, a);
         }
         // 4 x 4 transposes across the lanes (g, ju), g = 0..3: afterwards this thread holds i, f, g, o of unit ju at
         // rows 16 part + 4k + g, k = 0..3
