@@ -29,8 +29,9 @@
 
 constexpr int kWlTile = 64;            // batch rows per tile (= MMA N)
 // 64-wide K blocks per ring stage.  An mbarrier try_wait costs ~170 cycles even when the phase is already complete
-// (scripts/ubench/mma_issue.cu) and the tensor pipe drains meanwhile (tcgen05.mma issue behaves like a depth-1
-// queue), so waits must be rare: 6 K blocks = 24 MMAs of N = 64 (768 cycles of tensor work) per wait.
+// (scripts/ubench/mma_issue.cu: hidden behind queued MMAs in isolation, but visible as tensor-pipe bubbles in this
+// kernel, where four epilogue warps share the issuer's scheduler), so waits are rare: 6 K blocks = 24 MMAs of N = 64
+// (768 cycles of tensor work) per wait.
 #ifdef SVB_WL_RING_ALT                 // experiment (make ALT=1): finer stages, same bytes
 constexpr int kWlKbPerStage = 3;
 constexpr int kWlStages = 6;
