@@ -470,6 +470,20 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
     float dh[4] = {0.f, 0.f, 0.f, 0.f};          // reduced dL/dh of the tile whose gate backward is next
     int t = T - 1, j = 0;                        // tile being reduced
     int tg = T - 1, jg = 0;                      // tile whose gates are processed (lag tiles behind)
+    // per-tile bookkeeping kept short (it sits on the critical loop of the kernel, section 4.2 of DESIGN.md): offsets
+    // that depend on the thread only are formed once, ring slot / buffer indices are carried instead of divided out
+    const uint32_t own_t = own_a + row * 128 + ug * 16, recv_t = recv_a + row * 64 + ug * 8;
+    const size_t x_t = ((size_t)ns * kWbTile + row) * 32 + ug * 4;          // floats inside a (frame slot, tile) block
+    const size_t x_tile = (size_t)NS * kWbTile * 32;                         // floats per (frame slot, tile)
+    int xslot = (T - 1) % kWbXRing;                                          // t % kWbXRing, carried
+    int b3g = 0;                                                             // ig % 3 and (ig / 3) & 1, carried
+    uint32_t par3g = 0;
+    const int G_ = ug >> 1;
+    const uint32_t g_off_t = kWbOffG + (G_ >> 1) * 8192 + row * 128 + 8 * (ug & 1);
+    const uint32_t u_off_t = row * 128 + ((ug ^ (row & 7)) << 4);
+    uint32_t gsw[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) gsw[g] = g_off_t + (((4 * (G_ & 1) + g) ^ (row & 7)) << 4);
     for (int it = 0; it < total + lag; ++it) {
       float dn[4] = {0.f, 0.f, 0.f, 0.f};
       if (it < total) {
@@ -483,20 +497,21 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           // dX tile of the layer above (L2-resident ring), in flight while the partial sums arrive
           const int d = (int)(it % kWbDeps);
           WB_ACC(0, mbar_wait_warp(&dep_ready[d], (uint32_t)((it / kWbDeps) & 1)));
-          xrow = p.layer[l + 1].xring + (((size_t)((t % kWbXRing) * nt + j) * NS + ns) * kWbTile + row) * 32;
-          x0 = __ldcg(reinterpret_cast<const float4*>(xrow) + ug);
+          const float* xq = p.layer[l + 1].xring + (size_t)(xslot * nt + j) * x_tile + x_t;
+          xrow = xq - ug * 4;
+          x0 = __ldcg(reinterpret_cast<const float4*>(xq));
           __syncwarp();
           if (lane == 0) mbar_arrive(&dep_free[d]);
         } else if (is_R && t == T - 1 && j * kWbTile + row < p.B) {       // top layer, last frame: + dL/dh_last
           x0 = __ldg(reinterpret_cast<const float4*>(p.dh_last + (size_t)(j * kWbTile + row) * H + ns * 32) + ug);
         }
         if (!WB_ABL(64)) WB_ACC(2, mbar_wait_warp(&recv_full[buf], upar));   // own quarter + the three received quarters
-        const float4 o0 = lds_f4(own_a + buf * kWbOwnBytes + row * 128 + ug * 16);
+        const float4 o0 = lds_f4(own_t + buf * kWbOwnBytes);
         WL_STAMP(9);
         dn[0] = o0.x; dn[1] = o0.y; dn[2] = o0.z; dn[3] = o0.w;
 #pragma unroll
         for (int sl = 0; sl < 3; ++sl) {
-          const uint2 r = lds_u2(recv_a + buf * kWbRecvBytes + sl * kWbQuarterBytes + row * 64 + ug * 8);
+          const uint2 r = lds_u2(recv_t + buf * kWbRecvBytes + sl * kWbQuarterBytes);
           const float2 a0 = half2_to_float2(r.x), a1 = half2_to_float2(r.y);
           dn[0] += a0.x; dn[1] += a0.y; dn[2] += a1.x; dn[3] += a1.y;
         }
@@ -526,29 +541,28 @@ __global__ void __launch_bounds__(kWbThreads, 1) wbptt_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&x_done[buf]);
         }
-        if (++j == nt) { j = 0; --t; }
+        if (++j == nt) { j = 0; --t; if (--xslot < 0) xslot = kWbXRing - 1; }
       }
       if (lag == 0) { dh[0] = dn[0]; dh[1] = dn[1]; dh[2] = dn[2]; dh[3] = dn[3]; }
       if (is_R && it >= lag) {
         const int ig = it - lag;                   // tile (tg, jg)
         const int bufg = (int)(ig & 1);
         long long* tr = (trace_cta && tg == T / 2 && threadIdx.x == 0) ? trace_cta + jg * 16 : nullptr;
-        const int b3 = (int)(ig % 3);
-        const uint32_t par3 = (uint32_t)((ig / 3) & 1);
+        const int b3 = b3g;
+        const uint32_t par3 = par3g;
+        if (++b3g == 3) { b3g = 0; par3g ^= 1; }
         if (!WB_ABL(1024)) WB_ACC(4, mbar_wait_warp(&in_full[b3], par3));
         WL_STAMP(11);
         const uint32_t sb = stg_a + b3 * kWbIoBytes;
         const uint32_t cb = stg_a + kWbIo * kWbIoBytes + bufg * kWbCpBytes;
         if (!WB_ABL(2)) {
-          const int G = ug >> 1;                 // group of 8 units
-          const uint32_t g_off = (G >> 1) * 8192 + row * 128 + 8 * (ug & 1);
-          const uint32_t u_off = row * 128 + ((ug ^ (row & 7)) << 4);
+          const uint32_t u_off = u_off_t;
           const float4 cp4 = lds_f4(cb + u_off), dc4 = lds_f4(sb + kWbOffDc + u_off);
           uint32_t gaddr[4];
           uint2 gq[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            gaddr[g] = sb + kWbOffG + g_off + (((4 * (G & 1) + g) ^ (row & 7)) << 4);
+            gaddr[g] = sb + gsw[g];
             gq[g] = lds_u2(gaddr[g]);
           }
           const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcs[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
