@@ -523,8 +523,13 @@ def main():
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    # gradient all-reduce at N > 1: SVB_ALLREDUCE=peer (two-shot all-reduce over NVLink peer memory after backward,
+    # csrc/peer.cu), nccl_overlap (four NCCL buckets started from inside backward) or nccl (one NCCL call after backward)
+    ar_mode = os.environ.get("SVB_ALLREDUCE", "nccl_overlap")
+    if os.environ.get("SVB_ALLREDUCE_OVERLAP", "1") == "0" and ar_mode == "nccl_overlap":
+        ar_mode = "nccl"
     reducer = None
-    if world > 1 and os.environ.get("SVB_ALLREDUCE_OVERLAP", "1") != "0":
+    if world > 1 and ar_mode == "nccl_overlap":
         # default at N > 1: the gradient all-reduce runs in four buckets started from inside backward, beside the
         # remaining weight-gradient GEMMs (SVB_ALLREDUCE_OVERLAP=0: one all-reduce after backward)
         from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
@@ -548,7 +553,7 @@ def main():
             return loss
         loss.backward()
         if world > 1:
-            allreduce_gradients(params)
+            allreduce_gradients(params, peer=(ar_mode == "peer"))
         return loss
 
     def full_step():

@@ -94,11 +94,13 @@ int svb_set_ge2e_tensor_cores(int on);
  * single-device).  `peer_ptrs_dev` is a DEVICE array of `world` float pointers: the same symmetric buffer on every rank
  * (torch.distributed._symmetric_memory: handle.buffer_ptrs_dev).  The caller separates writes and reads of the buffers
  * with the handle's barrier.  Sums are taken in rank order (identical on every rank).
- *   svb_peer_gather: out[r * n + i] = peer_r[offset + i]                      (centroid all-gather)
+ *   svb_peer_gather: out[r * n + i] = peer_r[offset + r * rank_stride + i]    (centroid all-gather: rank_stride 0; second
+ *                    shot of the gradient all-reduce: rank r's reduced slice lives at r * slice in ITS buffer)
  *   svb_peer_reduce: seg_out[i] = sum_r peer_r[offset + seg_offset + i], tail_out[k] = sum_r peer_r[offset + tail_offset + k]
  *                    (this rank's rows of the centroid gradient + the loss / dw / db scalars)
  * Lengths and offsets in floats, multiples of 4 except the tail (<= 256 floats). */
-int svb_peer_gather(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t n_floats, float* out, void* stream);
+int svb_peer_gather(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t rank_stride_floats, size_t n_floats,
+                    float* out, void* stream);
 int svb_peer_reduce(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t seg_offset, size_t seg_floats,
                     size_t tail_offset, int tail_floats, float* seg_out, float* tail_out, void* stream);
 /* Weight gradients of the late frames beside the persistent BPTT kernel (csrc/lstm.cu): 1 (default; env

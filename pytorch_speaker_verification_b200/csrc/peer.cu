@@ -3,7 +3,9 @@
 // other's centroids and centroid-gradient partials with plain loads instead of going through NCCL (an all-gather of
 // 65 KB and an all-reduce of 524 KB per step at 8 GPUs: two collectives whose cost is latency, not bandwidth).
 // New functionality: the reference (speech_embedder_net.py:43-49) is single-device.  Both kernels add in RANK ORDER:
-// every rank computes bit-identical sums, run to run.
+// every rank computes bit-identical sums, run to run.  The same two kernels make a two-shot ALL-REDUCE of the 48.5 MB of
+// parameter gradients (reduce-scatter: every rank sums its slice over all peers in place; all-gather: every rank reads
+// the reduced slices back), see dist.PeerExchange.allreduce_.
 #include "../../include/svb200.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,14 +13,14 @@
 namespace svb {
 void set_error(const char* what, cudaError_t e);
 
-// out[r * n + i] = peer_r[off + i]   (n % 4 == 0, 16-byte aligned)
+// out[r * n + i] = peer_r[off + r * rank_stride + i]   (n % 4 == 0, 16-byte aligned)
 __global__ void __launch_bounds__(256) peer_gather_kernel(const float* const* __restrict__ peers, int world, size_t off,
-                                                          size_t n, float* __restrict__ out) {
+                                                          size_t rank_stride, size_t n, float* __restrict__ out) {
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 * world; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / n4);
     const size_t k = i - (size_t)r * n4;
-    const float4 v = *(reinterpret_cast<const float4*>(peers[r] + off) + k);
+    const float4 v = *(reinterpret_cast<const float4*>(peers[r] + off + (size_t)r * rank_stride) + k);
     reinterpret_cast<float4*>(out)[i] = v;
   }
 }
@@ -46,16 +48,16 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const float* const* __
 }  // namespace svb
 using namespace svb;
 
-extern "C" int svb_peer_gather(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t n_floats, float* out,
-                               void* stream) {
-  if (!peer_ptrs_dev || !out || world < 1 || (n_floats & 3) || (offset_floats & 3)) {
+extern "C" int svb_peer_gather(const void* peer_ptrs_dev, int world, size_t offset_floats, size_t rank_stride_floats,
+                               size_t n_floats, float* out, void* stream) {
+  if (!peer_ptrs_dev || !out || world < 1 || (n_floats & 3) || (offset_floats & 3) || (rank_stride_floats & 3)) {
     set_error("svb_peer_gather: bad argument (lengths and offsets in multiples of 4 floats)", cudaSuccess);
     return SVB_ERR_ARG;
   }
   const size_t n4 = n_floats / 4 * world;
   const unsigned grid = (unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592);
   peer_gather_kernel<<<grid ? grid : 1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float* const*>(peer_ptrs_dev), world, offset_floats, n_floats, out);
+      static_cast<const float* const*>(peer_ptrs_dev), world, offset_floats, rank_stride_floats, n_floats, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("svb_peer_gather", e); return SVB_ERR_CUDA; }
   return SVB_OK;

@@ -404,9 +404,41 @@ def _peer_gather(anchor: torch.Tensor, peer_ptrs_dev: int, world: int, offset: i
     """out[r, i] = peer_r[offset + i]: `anchor` is this rank's symmetric buffer (device / stream of the launch)."""
     out = torch.empty(int(world), int(n), dtype=torch.float32, device=anchor.device)
     with torch.cuda.device(anchor.device):
-        check(_lib.lib().svb_peer_gather(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(int(offset)), _sz(int(n)),
-                                         ptr(out), stream_ptr(anchor.device)), "svb_peer_gather")
+        check(_lib.lib().svb_peer_gather(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(int(offset)), _sz(0),
+                                         _sz(int(n)), ptr(out), stream_ptr(anchor.device)), "svb_peer_gather")
     return out
+
+
+def peer_allreduce_(flat, buf, peer_ptrs_dev, world, rank, barrier):
+    """In-place SUM all-reduce of the contiguous float32 tensor ``flat`` through the symmetric buffer ``buf`` (>= numel
+    padded to 4 * world floats) in two shots over NVLink peer memory: every rank sums ITS slice over all peers in place
+    (svb_peer_reduce), then reads all reduced slices back (svb_peer_gather).  Sums in rank order: bit-identical on every
+    rank.  ``barrier(channel)`` is the symmetric-memory handle's device-side barrier."""
+    n = flat.numel()
+    sl = (n + 4 * world - 1) // (4 * world) * 4                 # floats per slice
+    if buf.numel() < sl * world:
+        raise SvbError("peer_allreduce_: symmetric buffer too small")
+    L = _lib.lib()
+    with torch.cuda.device(flat.device):
+        st = stream_ptr(flat.device)
+        buf[:n].copy_(flat.reshape(-1))
+        if sl * world > n:
+            buf[n:sl * world].zero_()
+        barrier(0)                                                  # every rank's gradients are in its buffer
+        mine = ctypes.c_void_p(buf.data_ptr() + 4 * rank * sl)
+        check(L.svb_peer_reduce(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(0), _sz(rank * sl), _sz(sl), _sz(0), 0,
+                                mine, None, st), "svb_peer_reduce")
+        barrier(1)                                                  # every rank's slice is reduced
+        if sl * world == n:
+            out = flat.reshape(-1)
+        else:
+            out = torch.empty(sl * world, dtype=torch.float32, device=flat.device)
+        check(L.svb_peer_gather(ctypes.c_void_p(int(peer_ptrs_dev)), int(world), _sz(0), _sz(sl), _sz(sl), ptr(out), st),
+              "svb_peer_gather")
+        if out.data_ptr() != flat.data_ptr():
+            flat.reshape(-1).copy_(out[:n])
+        barrier(2)                                                  # nobody still reads a buffer that the next call overwrites
+    return flat
 
 
 _op("peer_gather(Tensor anchor, int peer_ptrs_dev, int world, int offset, int n) -> Tensor", _peer_gather,

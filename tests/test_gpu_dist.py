@@ -75,6 +75,21 @@ def _worker(rank, world, port, out):
     for _ in range(3):                               # buffer reuse across steps (two barriers per step)
         l2 = glp(emb.detach().reshape(hi - lo, M, -1))
         assert abs(l2.item() - lossP.item()) < 1e-6 * abs(lossP.item())
+    # two-shot all-reduce of the flat gradient buffer over NVLink peer memory (rank-ordered sums) against NCCL's
+    net.zero_grad()
+    crit.zero_grad()
+    emb = net(x[lo:hi].reshape(-1, T, 40).cuda())
+    GlobalGE2ELoss(crit)(emb.reshape(hi - lo, M, -1)).backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    allreduce_gradients(list(net.parameters()), peer=True)
+    from pytorch_speaker_verification_b200 import dist as svb_dist
+    assert any(v is not None for v in svb_dist._PEER_ALLREDUCE.values()), "peer all-reduce was not used"
+    for p, g in zip(net.parameters(), local):
+        ref_sum = g.clone()
+        dist.all_reduce(ref_sum, op=dist.ReduceOp.SUM)
+        assert torch.allclose(p.grad, ref_sum, rtol=1e-6, atol=1e-9)
+    for p, r in zip(net.parameters(), first):
+        assert torch.equal(p.grad, r) or float((p.grad - r).norm() / r.norm()) < 1e-6
     # the same step with the bucketed all-reduce started from inside backward: identical sums
     from pytorch_speaker_verification_b200.dist import OverlappedGradReducer
     ref = first                                  # (same GE2E mode: the sums must be bit-identical)
