@@ -109,3 +109,19 @@ def test_speaker_shard():
     assert [speaker_shard(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
     with pytest.raises(ValueError):
         speaker_shard(10, 0, 4)
+
+
+def test_flat_view_recognises_slices_of_one_storage():
+    """allreduce_gradients reduces ONE flat tensor when the gradients are contiguous slices that tile one allocation
+    (what svb200::embedder_bwd returns: custom-op outputs, no autograd ``_base``), and refuses anything else."""
+    from pytorch_speaker_verification_b200.dist import _flat_view
+    flat = torch.arange(24, dtype=torch.float32)
+    parts = [flat[0:6].view(2, 3), flat[6:10], flat[10:24].view(7, 2)]
+    parts = [torch.as_strided(flat, p.shape, p.stride(), p.storage_offset()) for p in parts]      # no _base, as from an op
+    v = _flat_view(parts[::-1])
+    assert v is not None and v.numel() == 24 and v.data_ptr() == flat.data_ptr()
+    v.mul_(2)
+    assert float(parts[1][0]) == 12.0
+    assert _flat_view([parts[0], parts[2]]) is None                                     # gap
+    assert _flat_view([parts[0], torch.zeros(4)]) is None                               # different storage
+    assert _flat_view([flat[0:6].view(2, 3).t(), flat[6:24]]) is None                  # non-contiguous member
