@@ -385,6 +385,16 @@ def secondary_benchmarks(torch, dist, svb, _lib, I, net, dev, rank, world, n_ext
     return out
 
 
+def workload_config(world):
+    """`config` of every arm (ours, --impl reference, --impl reference-cuda): the SAME dict for the same N, so that the
+    driver's same-config check compares like with like; what is specific to an arm goes to its `arm_notes`."""
+    return {"workload": "GE2E train step, 64 speakers x 10 utts x 160 frames x 40 mel per GPU "
+                        "(BASELINE configs[1]; global batch = 64 x n_gpus speakers, configs[2] at 8)",
+            "network": "3-layer LSTM 40->768, Linear 768->256, L2 norm; GE2E w=10 b=-5; reference init seed 0",
+            "parallelism": f"dp{world} by speaker group" if world > 1 else "single GPU",
+            "l2": "GPU arms: 192 MiB buffer written between timed iterations (untimed)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -394,8 +404,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "utts/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "GE2E train step N=64 x M=10, 160 frames x 40 mel (BASELINE configs[1])",
-                       "sample": sample},
+            "config": workload_config(args.gpus),
+            "arm_notes": {"sample": sample, "where": "rank 0's host cores (one process whatever N)"},
             "cpu_baseline": {"value": rate, "unit": "utts/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "utts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -453,8 +463,7 @@ def run_reference_cuda(args, rank, local_rank):
     line = {"impl": "reference-cuda", "metric": METRIC, "value": best["utts_per_s"], "unit": "utts/s", "n_gpus": 1,
             "steps": steps, "warmup": warm, "ms_per_step": best["ms_per_step_fwd_loss_bwd"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cuDNN, TF32 allowed)", "data": "synthetic",
-            "config": {"workload": "GE2E train step N=64 x M=10, 160 frames x 40 mel (BASELINE configs[1])",
-                       "l2": "192 MiB buffer written between timed iterations (untimed)"},
+            "config": workload_config(1),
             "e2e": {"value": best["utts_per_s_e2e"], "unit": "utts/s", "ms_per_step": best["ms_per_step_e2e"],
                     "h2d_bytes_per_step": B * T_FR * NMELS * 4, "d2h_bytes_per_step": 4},
             "gpu_baseline": blk}
@@ -710,14 +719,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": "GE2E train step, 64 speakers x 10 utts x 160 frames x 40 mel per GPU "
-                                   "(BASELINE configs[1]; global batch = 64 x n_gpus speakers, configs[2] at 8)",
-                       "model": "3-layer LSTM 40->768, Linear 768->256, L2 norm; GE2E w=10 b=-5; reference init seed 0",
-                       "precision": "forward GEMMs fp16 x fp16 (single term), MUFU.TANH gates; BPTT GEMMs bf16; "
-                                    "fp32 accumulate/cell state/loss",
-                       "parallelism": f"dp{world} by speaker group" if world > 1 else "single GPU",
-                       "l2": "192 MiB buffer written between timed iterations (untimed)",
-                       "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
+            "config": workload_config(world),
+            "arm_notes": {"precision": "forward GEMMs fp16 x fp16 (single term), MUFU.TANH gates; BPTT GEMMs bf16; "
+                                       "fp32 accumulate/cell state/loss",
+                          "e2e_step": "H2D pinned batch + zero_grad + fwd + GE2E + bwd + clip_grad_norm_ x2 + SGD + D2H loss"},
             "e2e": {"value": utts / (ms_e2e * 1e-3), "unit": "utts/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": (launch_count[0] if launch_count else launches_per_step(world)) * args.steps,
